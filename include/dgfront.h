@@ -1,0 +1,83 @@
+/* dgfront.h — C API of the host front end that stands in for the reference's Gmsh-based set-up
+ * (src/dgalerkin.cpp, src/configParser.cpp, Mesh::Mesh in src/Mesh.cpp:20-435) in an environment without
+ * the Gmsh SDK. It produces exactly the arrays the reference's Mesh object holds and exposes them as a
+ * dgb_desc (include/dgb.h). Host-only code; runs once per simulation.
+ */
+#ifndef DGFRONT_H
+#define DGFRONT_H
+
+#include <stdint.h>
+#include "dgb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dgf_model dgf_model; /* what gmsh::open leaves in memory */
+typedef struct dgf_mesh dgf_mesh;   /* the reference's Mesh object, as plain arrays */
+
+#define DGF_MAX_SOURCES 64
+#define DGF_MAX_INIT 32
+#define DGF_MAX_PHYS 64
+
+/* struct Config, include/configParser.h:7-41 */
+typedef struct dgf_config {
+    double timeStart, timeEnd, timeStep, timeRate;
+    char elementType[64];
+    char timeIntMethod[64];
+    char saveFile[512];
+    int32_t numThreads;
+    double v0[3], rho0, c0;
+    int32_t nSources;
+    double sources[DGF_MAX_SOURCES][9]; /* pole, x, y, z, size, amp, freq, phase, duration (configParser.cpp:81-100) */
+    int32_t nInit;
+    double initConditions[DGF_MAX_INIT][6]; /* 0, x, y, z, size, amp (configParser.cpp:110) */
+    int32_t nPhysBC;
+    int32_t physBCTag[DGF_MAX_PHYS];  /* ascending physical tag (std::map order, configParser.h:23) */
+    int32_t physBCType[DGF_MAX_PHYS]; /* 0 "Absorbing", 1 "Reflecting" */
+} dgf_config;
+
+const char* dgf_last_error(void);
+
+/* gmsh::open + (optionally) `gmsh -order p`: order <= 1 keeps the file's order */
+dgf_model* dgf_open_msh(const char* path, int order);
+/* synthetic cube of n^3 x 6 Kuhn tetrahedra on [lo,hi]^3 at `order` (BASELINE config 5) */
+dgf_model* dgf_make_cube(int n, double lo, double hi, int order);
+void dgf_model_free(dgf_model* m);
+int dgf_model_dimension(const dgf_model* m);
+
+/* config::parseConfig (src/configParser.cpp:30-150); the model provides the physical-group names */
+int dgf_parse_config(const char* path, const dgf_model* model, dgf_config* out);
+/* a default-initialised config (include/configParser.h defaults) for programmatic use */
+void dgf_default_config(dgf_config* out);
+
+/* Mesh::Mesh (src/Mesh.cpp:20-435) */
+dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg);
+void dgf_mesh_free(dgf_mesh* mesh);
+const dgb_desc* dgf_mesh_desc(const dgf_mesh* mesh); /* pointers stay valid until dgf_mesh_free */
+const double* dgf_mesh_node_coords(const dgf_mesh* mesh); /* [K*Np][3], what gmsh::model::mesh::getNode returns per DG node */
+const int32_t* dgf_mesh_el_tags(const dgf_mesh* mesh);     /* [K] */
+const int32_t* dgf_mesh_el_node_tags(const dgf_mesh* mesh); /* [K*Np] */
+const int32_t* dgf_mesh_face_nodes(const dgf_mesh* mesh);   /* [Nf][Nfp] local node ids of each local face */
+
+/* initial condition, src/dgalerkin.cpp:36-50 :  u[0][n] += amp*exp(-|x_n - x0|^2/size) ; u is [4][K*Np], zeroed first */
+void dgf_initial_condition(const dgf_mesh* mesh, const dgf_config* cfg, double* u);
+/* source node sets, src/solver.cpp:197-210 : nodes with |x_n - x_s|^2 < size^2.
+ * Returns the total count; offsets has nSources+1 entries; nodeIdx may be NULL to query the size. */
+int dgf_source_nodes(const dgf_mesh* mesh, const dgf_config* cfg, int32_t* offsets, int32_t* nodeIdx);
+/* Replays the floating-point loop header of src/solver.cpp:216-223. Returns the number of executed steps;
+ * if snapshotSteps != NULL it receives up to capacity step indices at which the reference takes a snapshot
+ * and *nSnapshots their count. */
+int dgf_time_loop(const dgf_config* cfg, int32_t* snapshotSteps, int capacity, int* nSnapshots);
+/* nearest DG node to a point (probe placement helper; probes are a new capability) */
+int dgf_nearest_node(const dgf_mesh* mesh, double x, double y, double z);
+
+/* Gmsh-compatible output: appends $ElementNodeData views to `path` (MSH 4.0 ASCII, after a copy of the mesh
+ * on first use), the way gmsh::view::write(tag, saveFile, append=true) does at src/solver.cpp:289-291. */
+int dgf_write_views(const char* path, const dgf_model* model, const dgf_mesh* mesh, const dgf_config* cfg,
+                    int nSnap, const int32_t* snapStep, const double* snapTime, const double* snapU /* [nSnap][4][K*Np] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGFRONT_H */
