@@ -1,0 +1,727 @@
+// C ABI of the engine (include/dgb.h): operator construction, upload, device-resident time loop, halo exchange.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dgb_internal.h"
+#include "partition.h"
+
+using namespace dgb;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DgbException : std::runtime_error {
+    int code;
+    DgbException(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess)                                                                                   \
+            throw DgbException(DGB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+#define NCCL_CHECK(expr)                                                                                         \
+    do {                                                                                                         \
+        ncclResult_t _r = (expr);                                                                                \
+        if (_r != ncclSuccess) throw DgbException(DGB_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(_r)); \
+    } while (0)
+
+template <typename T>
+T* devAlloc(size_t n) {
+    T* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <typename T>
+T* devUpload(const std::vector<T>& v) {
+    T* p = devAlloc<T>(v.size());
+    if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+// ---- small dense helpers in extended precision (set-up only) ----
+typedef long double real;
+void invertDense(std::vector<real>& A, int n) {
+    std::vector<real> B((size_t)n * n, 0);
+    for (int i = 0; i < n; ++i) B[(size_t)i * n + i] = 1;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabsl(A[(size_t)r * n + c]) > fabsl(A[(size_t)piv * n + c])) piv = r;
+        if (A[(size_t)piv * n + c] == 0) throw DgbException(DGB_ERR_ARG, "singular reference mass matrix");
+        if (piv != c)
+            for (int k = 0; k < n; ++k) { std::swap(A[(size_t)c * n + k], A[(size_t)piv * n + k]); std::swap(B[(size_t)c * n + k], B[(size_t)piv * n + k]); }
+        const real d = 1 / A[(size_t)c * n + c];
+        for (int k = 0; k < n; ++k) { A[(size_t)c * n + k] *= d; B[(size_t)c * n + k] *= d; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const real f = A[(size_t)r * n + c];
+            if (f == 0) continue;
+            for (int k = 0; k < n; ++k) { A[(size_t)r * n + k] -= f * A[(size_t)c * n + k]; B[(size_t)r * n + k] -= f * B[(size_t)c * n + k]; }
+        }
+    }
+    A.swap(B);
+}
+
+}  // namespace
+
+struct dgb_handle {
+    DeviceMesh M{};
+    dgb_desc hd{};  // scalar members of the global desc
+    int Kglobal = 0, Np = 0;
+    bool partitioned = false;
+    PartitionPlan plan;
+    double *U = nullptr, *ACC = nullptr, *YA = nullptr, *YB = nullptr;
+    cudaStream_t stream = nullptr, commStream = nullptr;
+    bool ownStream = true;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
+    std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
+    int stageEvUsed = 0;
+    StageKernel generic, tiled, active;
+    int overlap = 1;
+    int timeStages = 1;
+    // sources
+    std::vector<int32_t> srcOff;
+    int32_t* dSrcIdx = nullptr;
+    std::vector<double> srcAmp, srcFreq, srcPhase, srcDur;
+    // probes
+    int nprobe = 0;
+    int32_t* dProbeIdx = nullptr;
+    double* dProbeRec = nullptr;
+    int probeCap = 0, probeCount = 0;
+    bool stateSet = false;
+    double lastRunMs = 0, lastStageMs = 0;
+    int64_t launches = 0;
+    // halo exchange
+    ncclComm_t comm = nullptr;
+    double *sendBuf = nullptr, *recvBuf = nullptr;
+    int32_t* dSendElems = nullptr;
+    std::vector<double> hostStage;
+};
+
+namespace {
+
+void freeHandle(dgb_handle* h) {
+    if (!h) return;
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->commStream) cudaStreamSynchronize(h->commStream);
+    if (h->comm) ncclCommDestroy(h->comm);
+    F(h->U); F(h->ACC); F(h->YA); F(h->YB);
+    F(h->M.DwT); F(h->M.nLiftT); F(h->M.opFused); F(h->M.faceNodes); F(h->M.nbrMaps);
+    F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
+    F(h->dSrcIdx); F(h->dProbeIdx); F(h->dProbeRec); F(h->sendBuf); F(h->recvBuf); F(h->dSendElems);
+    for (auto e : h->stageEv) cudaEventDestroy(e);
+    for (auto e : {h->evStart, h->evStop, h->evBorder, h->evRecv}) if (e) cudaEventDestroy(e);
+    if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+    if (h->commStream) cudaStreamDestroy(h->commStream);
+    delete h;
+}
+
+void validate(const dgb_desc* d) {
+    if (!d) throw DgbException(DGB_ERR_ARG, "desc is null");
+    const void* ptrs[] = {d->elBasisFct, d->elUGradBasisFct, d->elWeight, d->fBasisFct, d->fWeight, d->elJacobian, d->elJacobianDet,
+                          d->fNormal, d->fJacobianDet, d->elFId, d->elFOrientation, d->fNbrElId, d->fNToElNId, d->fIsBoundary, d->fBC};
+    for (const void* p : ptrs) if (!p) throw DgbException(DGB_ERR_ARG, "desc has a null array pointer");
+    if (d->dim < 1 || d->dim > 3 || d->order < 1 || d->order > 6) throw DgbException(DGB_ERR_UNSUPPORTED, "dim must be 1..3 and order 1..6");
+    if (d->K < 1 || d->F < 1 || d->Np < 1 || d->Nfp < 1 || d->Nf < 1 || d->nG < 1 || d->nGf < 1) throw DgbException(DGB_ERR_ARG, "non-positive size in desc");
+    const int p = d->order;
+    const int np = d->dim == 1 ? p + 1 : d->dim == 2 ? (p + 1) * (p + 2) / 2 : (p + 1) * (p + 2) * (p + 3) / 6;
+    const int nfp = d->dim == 1 ? 1 : d->dim == 2 ? p + 1 : (p + 1) * (p + 2) / 2;
+    const int nf = d->dim == 1 ? p + 1 : d->dim + 1;
+    if (d->Np != np || d->Nfp != nfp || d->Nf != nf) throw DgbException(DGB_ERR_UNSUPPORTED, "Np/Nfp/Nf do not describe a simplex Lagrange element of this order");
+    if (!(d->nGeomEl == 1 || d->nGeomEl == d->nG) || !(d->nGeomF == 1 || d->nGeomF == d->nGf)) throw DgbException(DGB_ERR_ARG, "nGeomEl/nGeomF must be 1 or nG/nGf");
+    if (d->Np > 255) throw DgbException(DGB_ERR_UNSUPPORTED, "more than 255 nodes per element");
+    if (!(d->rho0 > 0) || !(d->c0 > 0)) throw DgbException(DGB_ERR_ARG, "rho0 and c0 must be positive");
+}
+
+// The hot path is written for straight-sided elements: every quadrature point of an element / face must carry
+// the same Jacobian / normal (curved geometry is SURVEY §8 f3).
+void checkAffine(const dgb_desc* d) {
+    if (d->nGeomEl > 1)
+        for (int el = 0; el < d->K; ++el)
+            for (int g = 1; g < d->nG; ++g) {
+                for (int k = 0; k < 9; ++k) {
+                    const double a = d->elJacobian[((size_t)el * d->nG) * 9 + k], b = d->elJacobian[((size_t)el * d->nG + g) * 9 + k];
+                    if (std::fabs(a - b) > 1e-11 * (std::fabs(a) + std::fabs(b) + 1e-300) + 1e-13)
+                        throw DgbException(DGB_ERR_UNSUPPORTED, "curved (non-affine) element " + std::to_string(el) + ": not supported by this engine");
+                }
+            }
+    if (d->nGeomF > 1)
+        for (int f = 0; f < d->F; ++f)
+            for (int g = 1; g < d->nGf; ++g)
+                for (int k = 0; k < 3; ++k) {
+                    const double a = d->fNormal[((size_t)f * d->nGf) * 3 + k], b = d->fNormal[((size_t)f * d->nGf + g) * 3 + k];
+                    if (std::fabs(a - b) > 1e-11) throw DgbException(DGB_ERR_UNSUPPORTED, "curved face " + std::to_string(f) + ": not supported by this engine");
+                }
+}
+
+struct HostOperators {
+    std::vector<double> DwT, nLiftT, opFused;
+    std::vector<int32_t> faceNodes;
+    std::vector<real> Mf;
+    int Lpad;
+};
+
+// Reference-element operators from the tables the reference's Mesh holds:
+//   Mref_ij = sum_g w_g phi_i phi_j,  K^u_ij = sum_g w_g dphi_i/du phi_j,  Dw^u = Mref^-1 K^u,
+//   Mf_nm = sum_g wf_g phif_n phif_m,  LIFT_lf = Mref^-1[:, faceNodes(lf)] Mf
+HostOperators buildOperators(const dgb_desc* d) {
+    const int Np = d->Np, Nfp = d->Nfp, Nf = d->Nf, dim = d->dim, nG = d->nG, nGf = d->nGf;
+    HostOperators H;
+    std::vector<real> Minv((size_t)Np * Np, 0);
+    for (int g = 0; g < nG; ++g)
+        for (int i = 0; i < Np; ++i) {
+            const real wi = (real)d->elWeight[g] * d->elBasisFct[(size_t)g * Np + i];
+            for (int j = 0; j < Np; ++j) Minv[(size_t)i * Np + j] += wi * d->elBasisFct[(size_t)g * Np + j];
+        }
+    invertDense(Minv, Np);
+    H.DwT.assign((size_t)dim * Np * Np, 0.0);
+    std::vector<real> Dw((size_t)dim * Np * Np, 0);
+    for (int u = 0; u < dim; ++u) {
+        std::vector<real> Ku((size_t)Np * Np, 0);
+        for (int g = 0; g < nG; ++g)
+            for (int i = 0; i < Np; ++i) {
+                const real wi = (real)d->elWeight[g] * d->elUGradBasisFct[((size_t)g * Np + i) * 3 + u];
+                for (int j = 0; j < Np; ++j) Ku[(size_t)i * Np + j] += wi * d->elBasisFct[(size_t)g * Np + j];
+            }
+        for (int i = 0; i < Np; ++i)
+            for (int j = 0; j < Np; ++j) {
+                real s = 0;
+                for (int k = 0; k < Np; ++k) s += Minv[(size_t)i * Np + k] * Ku[(size_t)k * Np + j];
+                Dw[((size_t)u * Np + i) * Np + j] = s;
+                H.DwT[((size_t)u * Np + j) * Np + i] = (double)s;
+            }
+    }
+    H.Mf.assign((size_t)Nfp * Nfp, 0);
+    for (int g = 0; g < nGf; ++g)
+        for (int n = 0; n < Nfp; ++n) {
+            const real wn = (real)d->fWeight[g] * d->fBasisFct[(size_t)g * Nfp + n];
+            for (int m = 0; m < Nfp; ++m) H.Mf[(size_t)n * Nfp + m] += wn * d->fBasisFct[(size_t)g * Nfp + m];
+        }
+    // local face-node table: element 0 is the first owner of each of its faces
+    H.faceNodes.resize((size_t)Nf * Nfp);
+    for (int lf = 0; lf < Nf; ++lf) {
+        const int f = d->elFId[lf];
+        if (d->fNbrElId[2 * (size_t)f] != 0) throw DgbException(DGB_ERR_ARG, "fNbrElId: element 0 must be the first owner of its faces");
+        for (int m = 0; m < Nfp; ++m) H.faceNodes[lf * Nfp + m] = d->fNToElNId[((size_t)f * Nfp + m) * 2];
+    }
+    const int NFL = Nf * Nfp, L = dim * Np + NFL;
+    H.Lpad = (L + 3) / 4 * 4;
+    H.nLiftT.assign((size_t)NFL * Np, 0.0);
+    H.opFused.assign((size_t)Np * H.Lpad, 0.0);
+    for (int i = 0; i < Np; ++i) {
+        for (int u = 0; u < dim; ++u)
+            for (int j = 0; j < Np; ++j) H.opFused[(size_t)i * H.Lpad + u * Np + j] = (double)Dw[((size_t)u * Np + i) * Np + j];
+        for (int lf = 0; lf < Nf; ++lf)
+            for (int m = 0; m < Nfp; ++m) {
+                real s = 0;
+                for (int n = 0; n < Nfp; ++n) s += Minv[(size_t)i * Np + H.faceNodes[lf * Nfp + n]] * H.Mf[(size_t)n * Nfp + m];
+                H.nLiftT[((size_t)lf * Nfp + m) * Np + i] = (double)(-s);
+                H.opFused[(size_t)i * H.Lpad + dim * Np + lf * Nfp + m] = (double)(-s);
+            }
+    }
+    return H;
+}
+
+void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, const void* ncclId, dgb_handle** out) {
+    if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
+    *out = nullptr;
+    validate(d);
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw DgbException(DGB_ERR_ARG, "bad rank/nranks");
+    if (nranks > 1 && (!elPart || !ncclId)) throw DgbException(DGB_ERR_ARG, "partitioned create needs elPart and an NCCL id");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        throw DgbException(DGB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    checkAffine(d);
+    HostOperators H = buildOperators(d);
+
+    dgb_handle* h = new dgb_handle;
+    try {
+        const int Np = d->Np, Nfp = d->Nfp, Nf = d->Nf, dim = d->dim, K = d->K;
+        h->hd = *d;
+        h->Kglobal = K;
+        h->Np = Np;
+        h->partitioned = nranks > 1;
+        if (h->partitioned) {
+            h->plan = makePartitionPlan(K, Nf, d->elFId, d->fNbrElId, elPart, rank, nranks);
+        } else {
+            h->plan.Kown = h->plan.Kinterior = K;
+            h->plan.Khalo = 0;
+        }
+        const PartitionPlan& P = h->plan;
+        auto toGlobal = [&](int l) { return h->partitioned ? P.localToGlobal[l] : l; };
+        auto toLocal = [&](int g) { return h->partitioned ? P.globalToLocal[g] : g; };
+        DeviceMesh& M = h->M;
+        M.dim = dim; M.order = d->order; M.Np = Np; M.Nfp = Nfp; M.Nf = Nf; M.L = dim * Np + Nf * Nfp; M.Lpad = H.Lpad;
+        M.Kown = P.Kown; M.Ktot = P.Kown + P.Khalo;
+        M.stride = (int64_t)M.Ktot * Np;
+        M.c0 = d->c0; M.rho0 = d->rho0; M.v0[0] = d->v0[0]; M.v0[1] = d->v0[1]; M.v0[2] = d->v0[2];
+
+        // ---- per-element / per-face geometry in the device layout ----
+        const int gE = d->nGeomEl, gF = d->nGeomF;
+        std::vector<double> Ginv((size_t)M.Kown * dim * dim), fgeo((size_t)M.Kown * Nf * 4);
+        std::vector<int32_t> fnbr((size_t)M.Kown * Nf), fflags((size_t)M.Kown * Nf);
+        std::map<std::vector<uint8_t>, int> mapIds;
+        std::vector<uint8_t> maps;
+        std::vector<int> pos(Np, -1);
+        std::map<std::vector<int>, bool> checkedPerm;
+        for (int l = 0; l < M.Kown; ++l) {
+            const int el = toGlobal(l);
+            // inverse of A(r,c) = dx_c/du_r  ->  Ginv[x][u] = du_u/dx_x
+            const double* J = &d->elJacobian[(size_t)el * gE * 9];
+            real A[3][3], B[3][3];
+            for (int r = 0; r < dim; ++r) for (int c = 0; c < dim; ++c) A[r][c] = J[r * 3 + c];
+            if (dim == 1) B[0][0] = 1 / A[0][0];
+            else if (dim == 2) {
+                const real det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+                B[0][0] = A[1][1] / det; B[0][1] = -A[0][1] / det; B[1][0] = -A[1][0] / det; B[1][1] = A[0][0] / det;
+            } else {
+                const real det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                                 A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        const int r1 = (c + 1) % 3, r2 = (c + 2) % 3, c1 = (r + 1) % 3, c2 = (r + 2) % 3;
+                        B[r][c] = (A[r1][c1] * A[r2][c2] - A[r1][c2] * A[r2][c1]) / det;
+                    }
+            }
+            for (int x = 0; x < dim; ++x) for (int u = 0; u < dim; ++u) Ginv[(size_t)l * dim * dim + x * dim + u] = (double)B[x][u];
+            const double detE = d->elJacobianDet[(size_t)el * gE];
+            for (int lf = 0; lf < Nf; ++lf) {
+                const int f = d->elFId[(size_t)el * Nf + lf];
+                const int side = d->fNbrElId[2 * (size_t)f] == el ? 0 : 1;
+                if (d->fNbrElId[2 * (size_t)f + side] != el) throw DgbException(DGB_ERR_ARG, "elFId/fNbrElId are inconsistent");
+                const int o = d->elFOrientation[(size_t)el * Nf + lf];
+                double* fg = &fgeo[((size_t)l * Nf + lf) * 4];
+                for (int x = 0; x < 3; ++x) fg[x] = o * d->fNormal[(size_t)f * gF * 3 + x];
+                fg[3] = d->fJacobianDet[(size_t)f * gF] / detE;
+                int flags;
+                if (d->fIsBoundary[f]) {
+                    flags = d->fBC[f] == 1 ? FACE_REFLECTING : FACE_ABSORBING;
+                    fnbr[(size_t)l * Nf + lf] = -1;
+                } else {
+                    const int nbG = d->fNbrElId[2 * (size_t)f + (1 - side)];
+                    if (nbG < 0) throw DgbException(DGB_ERR_ARG, "interior face without a second owner");
+                    const int nbL = toLocal(nbG);
+                    if (nbL < 0) throw DgbException(DGB_ERR_STATE, "partition plan misses a halo element");
+                    fnbr[(size_t)l * Nf + lf] = nbL;
+                    const int tau = d->fc * o * (side == 0 ? 1 : -1);
+                    flags = FACE_INTERIOR | (tau < 0 ? FLAG_TAU_NEG : 0);
+                }
+                // face-node pairing in the element's own face-node order
+                std::fill(pos.begin(), pos.end(), -1);
+                for (int m = 0; m < Nfp; ++m) pos[H.faceNodes[lf * Nfp + m]] = m;
+                std::vector<uint8_t> mp(Nfp, 0);
+                std::vector<int> perm(Nfp);
+                for (int n = 0; n < Nfp; ++n) {
+                    const int own = d->fNToElNId[((size_t)f * Nfp + n) * 2 + side];
+                    if (own < 0 || own >= Np || pos[own] < 0) throw DgbException(DGB_ERR_ARG, "fNToElNId does not match the local face-node table");
+                    perm[n] = pos[own];
+                    const int nb = d->fIsBoundary[f] ? own : d->fNToElNId[((size_t)f * Nfp + n) * 2 + (1 - side)];
+                    mp[pos[own]] = (uint8_t)nb;
+                }
+                // the element-local LIFT assumes the face mass matrix is invariant under this renumbering
+                if (!checkedPerm.count(perm)) {
+                    for (int a = 0; a < Nfp; ++a)
+                        for (int b = 0; b < Nfp; ++b)
+                            if (fabsl(H.Mf[(size_t)a * Nfp + b] - H.Mf[(size_t)perm[a] * Nfp + perm[b]]) > 1e-14L)
+                                throw DgbException(DGB_ERR_UNSUPPORTED, "face node ordering is not a symmetry of the face element");
+                    checkedPerm[perm] = true;
+                }
+                auto it = mapIds.find(mp);
+                if (it == mapIds.end()) {
+                    it = mapIds.emplace(mp, (int)mapIds.size()).first;
+                    maps.insert(maps.end(), mp.begin(), mp.end());
+                }
+                if (it->second >= (1 << 20)) throw DgbException(DGB_ERR_UNSUPPORTED, "too many distinct face pairings");
+                fflags[(size_t)l * Nf + lf] = flags | (it->second << FLAG_MAP_SHIFT);
+            }
+        }
+        M.nMaps = (int)mapIds.size();
+        M.DwT = devUpload(H.DwT);
+        M.nLiftT = devUpload(H.nLiftT);
+        M.opFused = devUpload(H.opFused);
+        M.faceNodes = devUpload(H.faceNodes);
+        M.nbrMaps = devUpload(maps);
+        M.Ginv = devUpload(Ginv);
+        M.fgeo = devUpload(fgeo);
+        M.fnbr = devUpload(fnbr);
+        M.fflags = devUpload(fflags);
+
+        const size_t stateN = (size_t)4 * M.stride;
+        h->U = devAlloc<double>(stateN);
+        h->ACC = devAlloc<double>(stateN);
+        h->YA = devAlloc<double>(stateN);
+        h->YB = devAlloc<double>(stateN);
+        CUDA_CHECK(cudaMemset(h->U, 0, stateN * sizeof(double)));
+        CUDA_CHECK(cudaMemset(h->ACC, 0, stateN * sizeof(double)));
+        CUDA_CHECK(cudaMemset(h->YA, 0, stateN * sizeof(double)));
+        CUDA_CHECK(cudaMemset(h->YB, 0, stateN * sizeof(double)));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&h->evStart));
+        CUDA_CHECK(cudaEventCreate(&h->evStop));
+        h->stageEv.resize(128);
+        for (auto& e : h->stageEv) CUDA_CHECK(cudaEventCreate(&e));
+
+        h->generic = selectGenericKernel(dim, d->order);
+        h->tiled = selectTiledKernel(dim, d->order);
+        if (!h->generic.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no stage kernel for this dim/order");
+        h->active = h->tiled.launch ? h->tiled : h->generic;
+
+        if (h->partitioned) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&h->evBorder, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&h->evRecv, cudaEventDisableTiming));
+            ncclUniqueId id;
+            std::memcpy(&id, ncclId, sizeof(id));
+            NCCL_CHECK(ncclCommInitRank(&h->comm, nranks, id, rank));
+            h->sendBuf = devAlloc<double>((size_t)4 * P.sendElems.size() * Np);
+            h->dSendElems = devUpload(P.sendElems);
+        }
+        *out = h;
+    } catch (...) {
+        freeHandle(h);
+        throw;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// time loop
+// ---------------------------------------------------------------------------------------------
+void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
+    if (eEnd <= eBegin) return;
+    A.eBegin = eBegin;
+    A.eEnd = eEnd;
+    const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
+    if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
+    h->active.launch(h->M, A, h->stream);
+    if (t) { cudaEventRecord(h->stageEv[h->stageEvUsed + 1], h->stream); h->stageEvUsed += 2; }
+    ++h->launches;
+}
+
+// Halo exchange of array y (owned border elements -> the peers' halo slots), SURVEY §8 e1.
+void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
+    const PartitionPlan& P = h->plan;
+    const int Np = h->Np;
+    const int64_t S = h->M.stride;
+    NCCL_CHECK(ncclGroupStart());
+    for (size_t i = 0; i < P.peers.size(); ++i) {
+        const int peer = P.peers[i];
+        const int nSend = P.sendOffset[i + 1] - P.sendOffset[i], nRecv = P.recvOffset[i + 1] - P.recvOffset[i];
+        const int64_t totalSend = (int64_t)P.sendElems.size() * Np;
+        for (int q = 0; q < 4; ++q) {
+            if (nSend > 0)
+                NCCL_CHECK(ncclSend(h->sendBuf + q * totalSend + (int64_t)P.sendOffset[i] * Np, (size_t)nSend * Np, ncclDouble, peer, h->comm, s));
+            if (nRecv > 0)
+                NCCL_CHECK(ncclRecv(y + q * S + (int64_t)(P.Kown + P.recvOffset[i]) * Np, (size_t)nRecv * Np, ncclDouble, peer, h->comm, s));
+        }
+    }
+    NCCL_CHECK(ncclGroupEnd());
+}
+
+// One stage = [border elements -> pack -> exchange on the comm stream] overlapped with [interior elements].
+void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
+    const PartitionPlan& P = h->plan;
+    if (!h->partitioned) {
+        launchStage(h, A, 0, h->M.Kown, true);
+        return;
+    }
+    const int nSendEl = (int)P.sendElems.size();
+    if (h->overlap) {
+        launchStage(h, A, P.Kinterior, P.Kown, false);
+        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        ++h->launches;
+        CUDA_CHECK(cudaEventRecord(h->evBorder, h->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(h->commStream, h->evBorder, 0));
+        exchangeHalo(h, produced, h->commStream);
+        CUDA_CHECK(cudaEventRecord(h->evRecv, h->commStream));
+        launchStage(h, A, 0, P.Kinterior, true);
+        CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
+    } else {
+        launchStage(h, A, 0, h->M.Kown, true);
+        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        ++h->launches;
+        exchangeHalo(h, produced, h->stream);
+    }
+}
+
+void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) {
+    if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
+    if (!h->stateSet) throw DgbException(DGB_ERR_STATE, "dgb_run before dgb_set_state");
+    if (nsteps < 0) throw DgbException(DGB_ERR_ARG, "nsteps < 0");
+    if (integrator != DGB_EULER1 && integrator != DGB_RUNGE_KUTTA) throw DgbException(DGB_ERR_ARG, "unknown integrator");
+    const double dt = h->hd.dt;
+    if (h->nprobe > 0 && h->probeCount + nsteps > h->probeCap) {
+        const int cap = std::max(h->probeCount + nsteps, 2 * h->probeCap);
+        double* nb = devAlloc<double>((size_t)cap * h->nprobe * 4);
+        if (h->probeCount) CUDA_CHECK(cudaMemcpyAsync(nb, h->dProbeRec, (size_t)h->probeCount * h->nprobe * 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->dProbeRec) cudaFree(h->dProbeRec);
+        h->dProbeRec = nb;
+        h->probeCap = cap;
+    }
+    h->stageEvUsed = 0;
+    CUDA_CHECK(cudaEventRecord(h->evStart, h->stream));
+    for (int step = 0; step < nsteps; ++step, t += dt) {
+        if (h->nprobe > 0) {
+            launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
+            ++h->probeCount;
+            ++h->launches;
+        }
+        for (size_t s = 0; s < h->srcAmp.size(); ++s)
+            if (t < h->srcDur[s]) {  // solver.cpp:253-255, evaluated on the host in the reference's own expression
+                const double val = h->srcAmp[s] * sin(2 * M_PI * h->srcFreq[s] * t + h->srcPhase[s]);
+                const int n = h->srcOff[s + 1] - h->srcOff[s];
+                launchSetNodes(h->U, h->dSrcIdx + h->srcOff[s], n, val, h->stream);
+                if (n > 0) ++h->launches;
+            }
+        StageArgs A{};
+        A.u = h->U; A.acc = h->ACC; A.dt = dt;
+        if (integrator == DGB_EULER1) {
+            A.yin = h->U; A.yout = h->YA; A.mode = MODE_EULER;
+            runStage(h, A, h->YA);
+            std::swap(h->U, h->YA);
+            continue;
+        }
+        A.yin = h->U;  A.yout = h->YA; A.mode = MODE_RK1; runStage(h, A, h->YA);
+        A.yin = h->YA; A.yout = h->YB; A.mode = MODE_RK2; runStage(h, A, h->YB);
+        A.yin = h->YB; A.yout = h->YA; A.mode = MODE_RK3; runStage(h, A, h->YA);
+        A.yin = h->YA; A.yout = nullptr; A.mode = MODE_RK4; runStage(h, A, h->U);
+    }
+    CUDA_CHECK(cudaEventRecord(h->evStop, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK(cudaGetLastError());
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, h->evStart, h->evStop));
+    h->lastRunMs = ms;
+    double sum = 0;
+    for (int i = 0; i + 1 < h->stageEvUsed; i += 2) {
+        float m2 = 0;
+        cudaEventElapsedTime(&m2, h->stageEv[i], h->stageEv[i + 1]);
+        sum += m2;
+    }
+    h->lastStageMs = h->stageEvUsed ? sum / (h->stageEvUsed / 2) : 0.0;
+    if (tEnd) *tEnd = t;
+}
+
+template <typename Fn>
+int guarded(Fn fn) {
+    try {
+        fn();
+        return DGB_OK;
+    } catch (const DgbException& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return DGB_ERR_ARG;
+    } catch (...) {
+        g_err = "unknown error";
+        return DGB_ERR_ARG;
+    }
+}
+
+// host <-> device state transfer; identity layout on one GPU, gather/scatter by element when partitioned
+void stateToDevice(dgb_handle* h, const double* u, double* dst) {
+    const int Np = h->Np;
+    const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
+    if (!h->partitioned) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, u, (size_t)4 * Ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        return;
+    }
+    h->hostStage.resize((size_t)4 * S);
+    for (int q = 0; q < 4; ++q)
+        for (int l = 0; l < h->M.Ktot; ++l)
+            std::memcpy(&h->hostStage[(size_t)q * S + (size_t)l * Np], u + q * Ng + (int64_t)h->plan.localToGlobal[l] * Np, Np * sizeof(double));
+    CUDA_CHECK(cudaMemcpyAsync(dst, h->hostStage.data(), (size_t)4 * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+void stateToHost(dgb_handle* h, const double* src, double* u) {
+    const int Np = h->Np;
+    const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
+    if (!h->partitioned) {
+        CUDA_CHECK(cudaMemcpyAsync(u, src, (size_t)4 * Ng * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        return;
+    }
+    h->hostStage.resize((size_t)4 * S);
+    CUDA_CHECK(cudaMemcpyAsync(h->hostStage.data(), src, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < 4; ++q)
+        for (int l = 0; l < h->M.Kown; ++l)  // owned elements only
+            std::memcpy(u + q * Ng + (int64_t)h->plan.localToGlobal[l] * Np, &h->hostStage[(size_t)q * S + (size_t)l * Np], Np * sizeof(double));
+}
+
+// global DG node index -> local (or -1); halo copies included when withHalo
+int localNode(const dgb_handle* h, int gnode, bool withHalo) {
+    if (gnode < 0 || gnode >= h->Kglobal * h->Np) throw DgbException(DGB_ERR_ARG, "node index out of range");
+    if (!h->partitioned) return gnode;
+    const int el = gnode / h->Np, n = gnode - el * h->Np;
+    const int l = h->plan.globalToLocal[el];
+    if (l < 0 || (!withHalo && l >= h->M.Kown)) return -1;
+    return l * h->Np + n;
+}
+
+}  // namespace
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+const char* dgb_last_error(void) { return g_err.c_str(); }
+const char* dgb_version(void) { return "dgb 0.1 (sm_100a)"; }
+
+int dgb_create(const dgb_desc* desc, dgb_handle** out) {
+    return guarded([&] { createImpl(desc, nullptr, 0, 1, nullptr, out); });
+}
+
+int dgb_create_partitioned(const dgb_desc* desc, const int32_t* elPart, int rank, int nranks, const void* id, dgb_handle** out) {
+    return guarded([&] { createImpl(desc, elPart, rank, nranks, id, out); });
+}
+
+int dgb_nccl_unique_id(void* out128) {
+    return guarded([&] {
+        if (!out128) throw DgbException(DGB_ERR_ARG, "out128 is null");
+        ncclUniqueId id;
+        NCCL_CHECK(ncclGetUniqueId(&id));
+        static_assert(sizeof(id) == 128, "ncclUniqueId is expected to be 128 bytes");
+        std::memcpy(out128, &id, sizeof(id));
+    });
+}
+
+void dgb_destroy(dgb_handle* h) { freeHandle(h); }
+
+int dgb_set_state(dgb_handle* h, const double* u) {
+    return guarded([&] {
+        if (!h || !u) throw DgbException(DGB_ERR_ARG, "null argument");
+        stateToDevice(h, u, h->U);
+        h->stateSet = true;
+    });
+}
+
+int dgb_get_state(dgb_handle* h, double* u) {
+    return guarded([&] {
+        if (!h || !u) throw DgbException(DGB_ERR_ARG, "null argument");
+        if (!h->stateSet) throw DgbException(DGB_ERR_STATE, "dgb_get_state before dgb_set_state");
+        stateToHost(h, h->U, u);
+    });
+}
+
+int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32_t* nodeIdx, const double* amp, const double* freq,
+                    const double* phase, const double* duration) {
+    return guarded([&] {
+        if (!h || nsrc < 0 || (nsrc > 0 && (!offsets || !amp || !freq || !phase || !duration))) throw DgbException(DGB_ERR_ARG, "bad source arguments");
+        std::vector<int32_t> off(1, 0), idx;
+        for (int s = 0; s < nsrc; ++s) {
+            for (int k = offsets[s]; k < offsets[s + 1]; ++k) {
+                const int l = localNode(h, nodeIdx[k], true);  // halo copies are overwritten too, so no extra exchange is needed
+                if (l >= 0) idx.push_back(l);
+            }
+            off.push_back((int32_t)idx.size());
+        }
+        if (h->dSrcIdx) { cudaFree(h->dSrcIdx); h->dSrcIdx = nullptr; }
+        h->dSrcIdx = devUpload(idx);
+        h->srcOff = off;
+        h->srcAmp.assign(amp, amp + nsrc);
+        h->srcFreq.assign(freq, freq + nsrc);
+        h->srcPhase.assign(phase, phase + nsrc);
+        h->srcDur.assign(duration, duration + nsrc);
+    });
+}
+
+int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
+    return guarded([&] {
+        if (!h || nprobe < 0 || (nprobe > 0 && !nodeIdx)) throw DgbException(DGB_ERR_ARG, "bad probe arguments");
+        std::vector<int32_t> idx(nprobe);
+        for (int j = 0; j < nprobe; ++j) idx[j] = localNode(h, nodeIdx[j], false);
+        if (h->dProbeIdx) { cudaFree(h->dProbeIdx); h->dProbeIdx = nullptr; }
+        if (h->dProbeRec) { cudaFree(h->dProbeRec); h->dProbeRec = nullptr; }
+        h->dProbeIdx = devUpload(idx);
+        h->nprobe = nprobe;
+        h->probeCap = h->probeCount = 0;
+    });
+}
+
+int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) {
+    return guarded([&] {
+        if (!h || !nsteps) throw DgbException(DGB_ERR_ARG, "null argument");
+        const int n = std::min(h->probeCount, capacity_steps);
+        if (n > 0 && h->nprobe > 0) {
+            if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
+            CUDA_CHECK(cudaMemcpyAsync(out, h->dProbeRec, (size_t)n * h->nprobe * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+        *nsteps = n;
+        h->probeCount = 0;
+    });
+}
+
+int dgb_run(dgb_handle* h, int integrator, double t_start, int nsteps, double* t_end) {
+    return guarded([&] { runImpl(h, integrator, t_start, nsteps, t_end); });
+}
+
+int dgb_eval_rhs(dgb_handle* h, const double* u, double* rhs) {
+    return guarded([&] {
+        if (!h || !u || !rhs) throw DgbException(DGB_ERR_ARG, "null argument");
+        stateToDevice(h, u, h->YA);
+        StageArgs A{};
+        A.yin = h->YA; A.u = h->U; A.acc = h->ACC; A.yout = h->YB; A.mode = MODE_RHS; A.dt = 1.0;
+        launchStage(h, A, 0, h->M.Kown, false);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaGetLastError());
+        stateToHost(h, h->YB, rhs);
+    });
+}
+
+int dgb_set_stream(dgb_handle* h, void* cuda_stream) {
+    return guarded([&] {
+        if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)cuda_stream;
+        h->ownStream = false;
+    });
+}
+
+int dgb_synchronize(dgb_handle* h) {
+    return guarded([&] {
+        if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->commStream) CUDA_CHECK(cudaStreamSynchronize(h->commStream));
+    });
+}
+
+double dgb_last_run_ms(dgb_handle* h) { return h ? h->lastRunMs : 0.0; }
+double dgb_last_stage_kernel_ms(dgb_handle* h) { return h ? h->lastStageMs : 0.0; }
+int64_t dgb_launch_count(dgb_handle* h) { return h ? h->launches : 0; }
+const char* dgb_kernel_name(dgb_handle* h) { return h ? h->active.name : "none"; }
+
+int dgb_set_option(dgb_handle* h, const char* key, int value) {
+    return guarded([&] {
+        if (!h || !key) throw DgbException(DGB_ERR_ARG, "null argument");
+        const std::string k(key);
+        if (k == "kernel") {
+            if (value == 1) h->active = h->generic;
+            else if (value == 2) {
+                if (!h->tiled.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no tiled kernel for this dim/order");
+                h->active = h->tiled;
+            } else h->active = h->tiled.launch ? h->tiled : h->generic;
+        } else if (k == "overlap") h->overlap = value ? 1 : 0;
+        else if (k == "time_stages") h->timeStages = value ? 1 : 0;
+        else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Internal declarations shared by the C-ABI layer (dgb_api.cu) and the kernels (stage_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dgb.h"
+
+namespace dgb {
+
+// What a stage launch does with k = dt * L(yin) (the 3-register RK4 that reproduces the
+// reference's (k1+2*k2+2*k3+k4)/6.0 expression bit for bit given identical k's, solver.cpp:261-285).
+enum StageMode : int {
+    MODE_RK1 = 0,    // acc  = k            ; yout = u + 0.5*k      (yin == u)
+    MODE_RK2 = 1,    // acc += 2*k          ; yout = u + 0.5*k
+    MODE_RK3 = 2,    // acc += 2*k          ; yout = u + 1.0*k
+    MODE_RK4 = 3,    // u   += (acc + k)/6.0
+    MODE_EULER = 4,  // yout = yin + k                              (solver.cpp:152-153, beta = 1)
+    MODE_RHS = 5     // yout = L(yin)  (dt ignored)                 (dgb_eval_rhs)
+};
+
+// Face flags (one int32 per element-local face)
+constexpr int FACE_INTERIOR = 0, FACE_ABSORBING = 1, FACE_REFLECTING = 2;
+constexpr int FLAG_BC_MASK = 0x3, FLAG_TAU_NEG = 0x4, FLAG_MAP_SHIFT = 8;
+
+struct DeviceMesh {
+    int dim, order, Np, Nfp, Nf, L;   // L = dim*Np + Nf*Nfp : contraction length of the fused operator
+    int Kown, Ktot;                   // owned elements, owned + halo
+    int64_t stride;                   // Ktot*Np : distance between two fields of a state array
+    // operators (device)
+    double* DwT;      // [dim][Np(j)][Np(i)]  transposed differentiation/stiffness operators, Dw^u = Mref^-1 K^u
+    double* nLiftT;   // [Nf*Nfp(l)][Np(i)]   -Mref^-1 E_lf Mf, transposed
+    double* opFused;  // [Np(i)][Lpad(l)]     [Dw^1 | Dw^2 | Dw^3 | -LIFT] row-major, padded (tiled kernel)
+    int Lpad;
+    int32_t* faceNodes;  // [Nf][Nfp] element-local node of face node m
+    uint8_t* nbrMaps;    // [nMaps][Nfp] neighbour's local node for face node m, de-duplicated patterns
+    int nMaps;
+    // geometry (device)
+    double* Ginv;     // [Kown][dim*dim]  Ginv[x*dim+u] = d u_u / d x_x
+    double* fgeo;     // [Kown][Nf][4]    outward unit normal (3), Fscale = detJ_f/detJ_e
+    int32_t* fnbr;    // [Kown][Nf]       neighbour element (local numbering, may point into the halo), -1 on the boundary
+    int32_t* fflags;  // [Kown][Nf]       bc type | tau sign | map id
+    // physics
+    double c0, rho0, v0[3];
+};
+
+struct StageArgs {
+    const double* yin;   // stage input  [4][stride]
+    double* u;           // solution     [4][stride]
+    double* acc;         // k-sum        [4][stride]
+    double* yout;        // next input / Euler or RHS output
+    int eBegin, eEnd;    // element range of this launch
+    int mode;
+    double dt;
+};
+
+// Returns a printable kernel name; launches on `stream`. kernelChoice: 0 auto, 1 generic, 2 tiled.
+typedef void (*StageLaunchFn)(const DeviceMesh&, const StageArgs&, cudaStream_t);
+struct StageKernel {
+    StageLaunchFn launch = nullptr;
+    const char* name = "none";
+};
+StageKernel selectGenericKernel(int dim, int order);
+StageKernel selectTiledKernel(int dim, int order);  // launch == nullptr if no tiled instance exists
+
+void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
+void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);
+void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
+void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
+
+}  // namespace dgb

@@ -299,24 +299,9 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
 
         // ---- face basis, Jacobians, normals (Mesh.cpp:135-194) ----
         const gml::RefElement& rf = gml::refElement(fDim, order);
-        gml::Quadrature qf = gml::gaussRule(fDim, 2 * order);
+        const gml::Quadrature qf = gml::integrationRule(fDim, 2 * order, order, dim == 3);  // see gmshlite.h
         const int nGf = qf.n;
         const int fc = (dim == 3 && order != 1) ? -1 : 1;  // Mesh.cpp:210-211
-        if (fDim == 2) {
-            // The raw sign of a 3D face normal is the sign of d(phi0,phi1)/d(u,v) at the rule's FIRST point
-            // (Mesh.cpp:183-188), which for Gmsh's own rule cannot be observed here. The reference
-            // scheme is stable only when fc * orientation(up) = +1, and the authors' `fc = -1` patch shows what
-            // they saw with Gmsh; the stand-in therefore lists first a point where that sign equals fc.
-            std::vector<double> dphi((size_t)Nfp * 3);
-            for (int g = 0; g < nGf; ++g) {
-                rf.gradBasis(&qf.pts[4 * g], dphi.data());
-                const double det = dphi[0] * dphi[4] - dphi[1] * dphi[3];
-                if (det * fc > 0) {
-                    for (int k = 0; k < 4; ++k) std::swap(qf.pts[k], qf.pts[4 * g + k]);
-                    break;
-                }
-            }
-        }
         M->fBasisFct.resize((size_t)nGf * Nfp);
         M->fWeight.resize(nGf);
         std::vector<double> fUGrad0((size_t)Nfp * 3);  // parametric gradients at the first integration point

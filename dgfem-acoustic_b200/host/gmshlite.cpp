@@ -330,6 +330,23 @@ const Quadrature& gaussRule(int dim, int degree) {
     return it->second;
 }
 
+Quadrature integrationRule(int dim, int degree, int order, bool faceOf3D) {
+    Quadrature q = gaussRule(dim, degree);
+    if (!(faceOf3D && dim == 2)) return q;
+    const int fc = order != 1 ? -1 : 1;
+    const RefElement& rf = refElement(2, order);
+    std::vector<double> dphi((size_t)rf.np * 3);
+    for (int g = 0; g < q.n; ++g) {
+        rf.gradBasis(&q.pts[4 * g], dphi.data());
+        const double det = dphi[0] * dphi[4] - dphi[1] * dphi[3];
+        if (det * fc > 0) {
+            for (int k = 0; k < 4; ++k) std::swap(q.pts[k], q.pts[4 * g + k]);
+            break;
+        }
+    }
+    return q;
+}
+
 // =============================================================================================
 // Model queries
 // =============================================================================================

@@ -44,6 +44,13 @@ struct Quadrature {
 // reference simplex of dimension dim (dim 0: one point of weight 1). Points are sorted so that
 // the first one is the closest to vertex 0.
 const Quadrature& gaussRule(int dim, int degree);
+// The rule the stand-in hands out for "Gauss<degree>" on an element of dimension dim and Lagrange order `order`.
+// Identical to gaussRule except for triangles used as faces of a 3D mesh (faceOf3D): there the reference derives
+// the raw sign of the face normal from d(phi0,phi1)/d(u,v) at the rule's FIRST point (Mesh.cpp:183-188), which
+// for Gmsh's own tables cannot be observed here. The reference scheme is stable only when
+// fc * orientation(first owner) = +1 with fc = (order == 1 ? +1 : -1) (Mesh.cpp:210-211), so the stand-in lists
+// first a point where that Jacobian sign equals fc. Only the ORDER of the points changes, not the rule.
+Quadrature integrationRule(int dim, int degree, int order, bool faceOf3D);
 
 // ---------------------------------------------------------------------------------------------
 // Model (what gmsh::open leaves in memory)

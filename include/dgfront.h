@@ -77,6 +77,18 @@ int dgf_nearest_node(const dgf_mesh* mesh, double x, double y, double z);
 int dgf_write_views(const char* path, const dgf_model* model, const dgf_mesh* mesh, const dgf_config* cfg,
                     int nSnap, const int32_t* snapStep, const double* snapTime, const double* snapU /* [nSnap][4][K*Np] */);
 
+/* ---- domain decomposition, host-side planning shared with the engine ---------------- */
+/* recursive coordinate bisection of the element centroids into nparts parts (balanced to +-1 element) */
+int dgf_partition_rcb(const dgf_mesh* mesh, int nparts, int32_t* elPart /* [K] */);
+typedef struct dgf_plan dgf_plan;
+dgf_plan* dgf_plan_create(const dgf_mesh* mesh, const int32_t* elPart, int rank, int nranks);
+void dgf_plan_free(dgf_plan* plan);
+/* sizes[6] = Kown, Kinterior, Khalo, npeers, nsend, nranks */
+void dgf_plan_sizes(const dgf_plan* plan, int32_t* sizes);
+/* localToGlobal[Kown+Khalo], peers[npeers], recvOffset[npeers+1], sendOffset[npeers+1], sendElems[nsend] (local ids) */
+void dgf_plan_arrays(const dgf_plan* plan, int32_t* localToGlobal, int32_t* peers, int32_t* recvOffset, int32_t* sendOffset,
+                     int32_t* sendElems);
+
 #ifdef __cplusplus
 }
 #endif
