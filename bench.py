@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the RK4 stage evaluation (BASELINE.json: DOF-updates/s per RK4 stage).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells n] [--order p]
+
+* workload (BASELINE config 5): synthetic cube of n^3 x 6 Kuhn tetrahedra (n = 62 -> 1 429 968 tets), order 4
+  (35 nodes / element, 50.05 M DG nodes, 200.2 M unknowns), absorbing boundary, c0 = 343, rho0 = 1.225,
+  Gaussian pressure pulse, dt = 0.1 h_min / (c0 (2p+1)), RK4. One bench "step" = one RK4 time step = 4 stage
+  launches over the whole mesh. DOF-updates/s = 4*K*Np unknowns x 4 stages x steps / time.
+* `value`  : state resident in HBM, timed with CUDA events inside the engine (dgb_last_run_ms), max over ranks.
+* `e2e`    : the user-facing call sequence through the C ABI from HOST buffers: dgb_set_state (pinned host ->
+             device), dgb_run(K steps), dgb_get_state (device -> pinned host), timed with a host clock around
+             the three synchronous calls, max over ranks.
+* `roofline`: the stage kernel against the HBM roof (algorithmic bytes) and, because order 4 is
+             FP64-bound, against the FP64 roof measured by profiles/microbench (DMMA/DFMA 37.1 TFLOP/s).
+* `cpu_baseline` / `--impl reference`: the reference's OWN sources (oracle/_ref/dgalerkin_ref) on the host cores
+             on a bounded sample of the same workload (falls back to the oracle's faithful mode, kind "port").
+N > 1 (launched by torchrun): the same mesh is partitioned over the ranks (recursive coordinate bisection), halo
+traces are exchanged with NCCL once per stage, overlapped with the interior elements ("strong" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "DOF-updates/s per RK4 stage"
+UNIT = "DOF-updates/s"
+FP64_PEAK_TFLOPS = 37.1  # profiles/microbench/r01_fp64_peaks_b200.txt (DMMA m8n8k4 sustained on this pool's B200)
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(pkg, cells, order, v0):
+    model = pkg.Model.make_cube(cells, -10.0, 10.0, order)
+    cfg = pkg.Config()
+    cfg.add_initial_condition(0.0, 0.0, 0.0, 1.0, 1.0)  # config.conf:57
+    mesh = pkg.Mesh(model, cfg)
+    c0, rho0 = 343.0, 1.225
+    dt = 0.1 * mesh.h_min() / (c0 * (2 * order + 1))
+    mesh.set_physics(c0=c0, rho0=rho0, v0=v0, dt=dt)
+    return model, cfg, mesh
+
+
+def alg_counts(mesh, v0_zero):
+    """Algorithmic bytes / flops of ONE stage launch over the whole mesh."""
+    K, Np, Nfp = mesh.K, mesh.Np, mesh.Nfp
+    bytes_stage = 34.0 * 4 * K * Np + 232.0 * K
+    flops_el = (12.0 if v0_zero else 24.0) * Np * Np + 32.0 * Np * Nfp + 160.0 * Nfp + 40.0 * Np
+    return bytes_stage, flops_el * K
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own sources on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------------------
+REF_CONF = """timeStart=0
+timeEnd={tend}
+timeStep={dt}
+timeRate=1000
+elementType=Lagrange
+timeIntMethod=Runge-Kutta
+numThreads={threads}
+v0_x = {v0x}
+v0_y = {v0y}
+v0_z = {v0z}
+rho0 = 1.225
+c0 = 343
+initialCondtition1 = gaussian, 0,0,0,1,1
+saveFile=out
+"""
+
+
+def time_reference(pkg, order, v0, steps, sample_cells=8):
+    """DOF-updates/s of the reference on a cube of sample_cells^3 x 6 tets at `order` (same generator, same physics).
+    Set-up (the reference's O(F^2) connectivity) is removed by differencing a 1-step and a (1+steps)-step run."""
+    ref_bin = ROOT / "oracle" / "_ref" / "dgalerkin_ref"
+    cores = os.cpu_count() or 1
+    model = pkg.Model.make_cube(sample_cells, -10.0, 10.0, 1)
+    cfg = pkg.Config()
+    mesh1 = pkg.Mesh(pkg.Model.make_cube(sample_cells, -10.0, 10.0, order), cfg)
+    K, Np = mesh1.K, mesh1.Np
+    dt = 0.1 * mesh1.h_min() / (343.0 * (2 * order + 1))
+    sample = f"cube {sample_cells}^3x6 = {K} tets, order {order}, {steps} RK4 steps"
+    if ref_bin.exists():
+        with tempfile.TemporaryDirectory() as wd:
+            msh = Path(wd) / "cube.msh"
+            model.write_msh(msh)
+            env = dict(os.environ, GMSHLITE_QUIET="1", GMSHLITE_ORDER=str(order), OMP_NUM_THREADS=str(cores))
+
+            def run(nsteps):
+                # the loop runs while t <= timeEnd: (nsteps - 0.5) * dt gives exactly nsteps iterations
+                conf = Path(wd) / f"c{nsteps}.conf"
+                conf.write_text(REF_CONF.format(tend=repr((nsteps - 0.5) * dt), dt=repr(dt), threads=cores, v0x=v0[0], v0y=v0[1], v0z=v0[2]))
+                t0 = time.perf_counter()
+                subprocess.run([str(ref_bin), str(msh), str(conf)], cwd=wd, env=env, check=True)
+                return time.perf_counter() - t0
+
+            t1 = run(1)
+            t2 = run(1 + steps)
+        sec = max(t2 - t1, 1e-9)
+        return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": sample + " (reference sources on Gmsh/Eigen stand-ins; set-up removed by differencing)", "seconds": sec}
+    from oracle.oracle_py import Oracle
+    mesh1.set_physics(c0=343.0, rho0=1.225, v0=v0, dt=dt)
+    orc = Oracle(mesh1, threads=cores)
+    u = mesh1.initial_condition() if cfg.c.nInit else np.zeros((4, mesh1.N))
+    orc.run(Oracle.FAITHFUL, pkg.RUNGE_KUTTA, u, 0.0, 1)  # builds the per-element matrices
+    t0 = time.perf_counter()
+    orc.run(Oracle.FAITHFUL, pkg.RUNGE_KUTTA, u, 0.0, steps)
+    sec = time.perf_counter() - t0
+    return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": sample + " (oracle, faithful mode)", "seconds": sec}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=62)
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--v0", type=float, nargs=3, default=[0.0, 0.0, 0.0])
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    pkg = graft.load_package()
+    workload = f"cube n={args.cells} ({args.cells ** 3 * 6} tets) order {args.order} RK4"
+    config = {"workload": workload, "cells": args.cells, "order": args.order, "v0": args.v0, "boundary": "absorbing",
+              "l2": "inputs larger than L2 (state arrays of 1.6 GB each)", "partition": "rcb" if world > 1 else "none"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        t0 = time.perf_counter()
+        res = None
+        for _ in range(max(1, min(args.warmup, 1))):
+            res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
+        wall = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": 0, "steps": steps, "warmup": args.warmup,
+                "ms_per_step": res["seconds"] / args.cpu_steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": wall}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model, cfg, mesh = build_workload(pkg, args.cells, args.order, args.v0)
+    K, Np = mesh.K, mesh.Np
+    unknowns = 4 * K * Np
+    if world > 1:
+        import ctypes as C
+        part = np.zeros(K, dtype=np.int32)
+        assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        if args.no_overlap:
+            eng.set_option("overlap", 0)
+    else:
+        eng = pkg.Engine(mesh)
+    if args.kernel:
+        eng.set_option("kernel", args.kernel)
+
+    # pinned host buffers for the end-to-end leg
+    host_u = torch.empty((4, mesh.N), dtype=torch.float64, pin_memory=True)
+    u_np = host_u.numpy()
+    u_np[...] = mesh.initial_condition()
+    t_sim = 0.0
+    eng.set_state(u_np)
+    barrier()
+    t_sim = eng.run(pkg.RUNGE_KUTTA, t_sim, args.warmup)
+    barrier()
+
+    launches0 = eng.launch_count
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_sim = eng.run(pkg.RUNGE_KUTTA, t_sim, args.steps)
+        ms = eng.last_run_ms
+        stage_ms = eng.last_stage_kernel_ms
+        barrier()
+    launches = eng.launch_count - launches0
+    ms = max_over_ranks(ms)
+    stage_ms = max_over_ranks(stage_ms)
+    value = unknowns * 4.0 * args.steps / (ms * 1e-3)
+    finite = bool(np.isfinite(eng.get_state(u_np)).all())
+
+    # end to end: host -> device, K steps, device -> host, through the public C ABI
+    barrier()
+    t0 = time.perf_counter()
+    eng.set_state(u_np)
+    eng.run(pkg.RUNGE_KUTTA, t_sim, args.steps)
+    eng.get_state(u_np)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = unknowns * 4.0 * args.steps / e2e_s
+    state_bytes = unknowns * 8
+
+    if rank == 0:
+        peaks, how = measured_peaks()
+        v0_zero = all(v == 0.0 for v in args.v0)
+        bytes_stage, flops_stage = alg_counts(mesh, v0_zero)
+        frac_work = 1.0  # the timed stage launch covers all elements on 1 GPU
+        if world > 1:
+            frac_work = 1.0 / world
+        gbs = bytes_stage * frac_work / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
+        tfl = flops_stage * frac_work / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
+        hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "kernel": eng.kernel_name, "finite": finite,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": state_bytes / args.steps,
+                    "what": "dgb_set_state(pinned host) + dgb_run(steps) + dgb_get_state(pinned host), host clock"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                         "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6.65 TB/s",
+                         "stage_kernel_ms": stage_ms, "alg_bytes_per_launch": bytes_stage * frac_work,
+                         "fp64": {"achieved": tfl, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tfl / FP64_PEAK_TFLOPS,
+                                  "alg_flops_per_launch": flops_stage * frac_work,
+                                  "peak_source": "profiles/microbench/r01_fp64_peaks_b200.txt (DMMA m8n8k4 sustained)"}},
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

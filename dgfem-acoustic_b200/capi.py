@@ -78,6 +78,7 @@ def load_front():
     lib.dgf_make_cube.restype = C.c_void_p
     lib.dgf_make_cube.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
     lib.dgf_model_free.argtypes = [C.c_void_p]
+    lib.dgf_write_msh.argtypes = [C.c_void_p, C.c_char_p]
     lib.dgf_model_dimension.argtypes = [C.c_void_p]
     lib.dgf_parse_config.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(DgfConfig)]
     lib.dgf_default_config.argtypes = [C.POINTER(DgfConfig)]
@@ -165,6 +166,10 @@ class Model:
     @property
     def dimension(self):
         return load_front().dgf_model_dimension(self.h)
+
+    def write_msh(self, path):
+        if load_front().dgf_write_msh(self.h, str(path).encode()) != 0:
+            raise FrontError(load_front().dgf_last_error().decode())
 
     def parse_config(self, path) -> Config:
         c = DgfConfig()

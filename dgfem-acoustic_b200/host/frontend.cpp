@@ -60,6 +60,50 @@ extern "C" dgf_model* dgf_make_cube(int n, double lo, double hi, int order) {
     }
 }
 
+extern "C" int dgf_write_msh(const dgf_model* mm, const char* path) {
+    try {
+        const gml::Model& m = mm->m;
+        std::FILE* fp = std::fopen(path, "w");
+        if (!fp) throw std::runtime_error(std::string("cannot open ") + path);
+        std::fprintf(fp, "$MeshFormat\n4 0 8\n$EndMeshFormat\n$PhysicalNames\n%zu\n", m.physNames.size());
+        for (auto& pn : m.physNames) std::fprintf(fp, "%d %d \"%s\"\n", pn.first.first, pn.first.second, pn.second.c_str());
+        std::fprintf(fp, "$EndPhysicalNames\n$Entities\n");
+        size_t cnt[4] = {0, 0, 0, 0};
+        for (auto& e : m.entities) cnt[e.dim]++;
+        std::fprintf(fp, "%zu %zu %zu %zu\n", cnt[0], cnt[1], cnt[2], cnt[3]);
+        for (int d = 0; d < 4; ++d)
+            for (auto& e : m.entities) {
+                if (e.dim != d) continue;
+                std::fprintf(fp, "%d 0 0 0 0 0 0 %zu", e.tag, e.phys.size());
+                for (int p : e.phys) std::fprintf(fp, " %d", p);
+                std::fprintf(fp, d == 0 ? "\n" : " 0\n");
+            }
+        std::fprintf(fp, "$EndEntities\n$Nodes\n1 %d\n", m.maxNodeTag);
+        int topDim = m.dimension(), topTag = 1;
+        for (auto& b : m.blocks) if (b.entityDim == topDim) topTag = b.entityTag;
+        std::fprintf(fp, "%d %d 0 %d\n", topTag, topDim, m.maxNodeTag);
+        for (int t = 1; t <= m.maxNodeTag; ++t) std::fprintf(fp, "%d %.17g %.17g %.17g\n", t, m.node(t)[0], m.node(t)[1], m.node(t)[2]);
+        size_t ne = 0;
+        for (auto& b : m.blocks) ne += b.tags.size();
+        std::fprintf(fp, "$EndNodes\n$Elements\n%zu %zu\n", m.blocks.size(), ne);
+        for (auto& b : m.blocks) {
+            const size_t nn = b.tags.empty() ? 0 : b.nodeTags.size() / b.tags.size();
+            std::fprintf(fp, "%d %d %d %zu\n", b.entityTag, b.entityDim, b.type, b.tags.size());
+            for (size_t e = 0; e < b.tags.size(); ++e) {
+                std::fprintf(fp, "%d", b.tags[e]);
+                for (size_t k = 0; k < nn; ++k) std::fprintf(fp, " %d", b.nodeTags[e * nn + k]);
+                std::fprintf(fp, " \n");
+            }
+        }
+        std::fprintf(fp, "$EndElements\n");
+        std::fclose(fp);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 extern "C" void dgf_model_free(dgf_model* m) { delete m; }
 extern "C" int dgf_model_dimension(const dgf_model* m) { return m ? m->m.dimension() : -1; }
 
