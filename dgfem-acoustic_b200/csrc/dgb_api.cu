@@ -12,6 +12,7 @@
 
 #include "dgb_internal.h"
 #include "partition.h"
+#include "tile_cfg.h"
 
 using namespace dgb;
 
@@ -117,7 +118,7 @@ void freeHandle(dgb_handle* h) {
     if (h->commStream) cudaStreamSynchronize(h->commStream);
     if (h->comm) ncclCommDestroy(h->comm);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
-    F(h->M.DwT); F(h->M.nLiftT); F(h->M.opFused); F(h->M.faceNodes); F(h->M.nbrMaps);
+    F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
     F(h->dSrcIdx); F(h->dProbeIdx); F(h->dProbeRec); F(h->sendBuf); F(h->recvBuf); F(h->dSendElems);
     for (auto e : h->stageEv) cudaEventDestroy(e);
@@ -166,10 +167,9 @@ void checkAffine(const dgb_desc* d) {
 }
 
 struct HostOperators {
-    std::vector<double> DwT, nLiftT, opFused;
+    std::vector<double> DwT, nLiftT, tiledOps;
     std::vector<int32_t> faceNodes;
     std::vector<real> Mf;
-    int Lpad;
 };
 
 // Reference-element operators from the tables the reference's Mesh holds:
@@ -215,20 +215,25 @@ HostOperators buildOperators(const dgb_desc* d) {
         if (d->fNbrElId[2 * (size_t)f] != 0) throw DgbException(DGB_ERR_ARG, "fNbrElId: element 0 must be the first owner of its faces");
         for (int m = 0; m < Nfp; ++m) H.faceNodes[lf * Nfp + m] = d->fNToElNId[((size_t)f * Nfp + m) * 2];
     }
-    const int NFL = Nf * Nfp, L = dim * Np + NFL;
-    H.Lpad = (L + 3) / 4 * 4;
+    const int NFL = Nf * Nfp;
     H.nLiftT.assign((size_t)NFL * Np, 0.0);
-    H.opFused.assign((size_t)Np * H.Lpad, 0.0);
-    for (int i = 0; i < Np; ++i) {
-        for (int u = 0; u < dim; ++u)
-            for (int j = 0; j < Np; ++j) H.opFused[(size_t)i * H.Lpad + u * Np + j] = (double)Dw[((size_t)u * Np + i) * Np + j];
+    for (int i = 0; i < Np; ++i)
         for (int lf = 0; lf < Nf; ++lf)
             for (int m = 0; m < Nfp; ++m) {
                 real s = 0;
                 for (int n = 0; n < Nfp; ++n) s += Minv[(size_t)i * Np + H.faceNodes[lf * Nfp + n]] * H.Mf[(size_t)n * Nfp + m];
                 H.nLiftT[((size_t)lf * Nfp + m) * Np + i] = (double)(-s);
-                H.opFused[(size_t)i * H.Lpad + dim * Np + lf * Nfp + m] = (double)(-s);
             }
+    // shared-memory image of the tiled DMMA kernel (stage_tiled.cu / tile_cfg.h)
+    int npp = 0, ldq = 0, ldf = 0;
+    if (tiledLayout(dim, d->order, &npp, &ldq, &ldf)) {
+        H.tiledOps.assign((size_t)3 * npp * ldq + (size_t)npp * ldf, 0.0);
+        for (int u = 0; u < 3; ++u)
+            for (int i = 0; i < Np; ++i)
+                for (int j = 0; j < Np; ++j) H.tiledOps[((size_t)u * npp + i) * ldq + j] = H.DwT[((size_t)u * Np + j) * Np + i];
+        double* L = H.tiledOps.data() + (size_t)3 * npp * ldq;
+        for (int i = 0; i < Np; ++i)
+            for (int l = 0; l < NFL; ++l) L[(size_t)i * ldf + l] = H.nLiftT[(size_t)l * Np + i];
     }
     return H;
 }
@@ -262,7 +267,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         auto toGlobal = [&](int l) { return h->partitioned ? P.localToGlobal[l] : l; };
         auto toLocal = [&](int g) { return h->partitioned ? P.globalToLocal[g] : g; };
         DeviceMesh& M = h->M;
-        M.dim = dim; M.order = d->order; M.Np = Np; M.Nfp = Nfp; M.Nf = Nf; M.L = dim * Np + Nf * Nfp; M.Lpad = H.Lpad;
+        M.dim = dim; M.order = d->order; M.Np = Np; M.Nfp = Nfp; M.Nf = Nf; M.L = dim * Np + Nf * Nfp;
         M.Kown = P.Kown; M.Ktot = P.Kown + P.Khalo;
         M.stride = (int64_t)M.Ktot * Np;
         M.c0 = d->c0; M.rho0 = d->rho0; M.v0[0] = d->v0[0]; M.v0[1] = d->v0[1]; M.v0[2] = d->v0[2];
@@ -349,7 +354,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         M.nMaps = (int)mapIds.size();
         M.DwT = devUpload(H.DwT);
         M.nLiftT = devUpload(H.nLiftT);
-        M.opFused = devUpload(H.opFused);
+        M.tiledOps = devUpload(H.tiledOps);
         M.faceNodes = devUpload(H.faceNodes);
         M.nbrMaps = devUpload(maps);
         M.Ginv = devUpload(Ginv);

@@ -32,8 +32,7 @@ struct DeviceMesh {
     // operators (device)
     double* DwT;      // [dim][Np(j)][Np(i)]  transposed differentiation/stiffness operators, Dw^u = Mref^-1 K^u
     double* nLiftT;   // [Nf*Nfp(l)][Np(i)]   -Mref^-1 E_lf Mf, transposed
-    double* opFused;  // [Np(i)][Lpad(l)]     [Dw^1 | Dw^2 | Dw^3 | -LIFT] row-major, padded (tiled kernel)
-    int Lpad;
+    double* tiledOps; // [3][NPP][LDQ] Dw^u then [NPP][LDF] -LIFT, zero padded: the shared-memory image of the tiled kernel
     int32_t* faceNodes;  // [Nf][Nfp] element-local node of face node m
     uint8_t* nbrMaps;    // [nMaps][Nfp] neighbour's local node for face node m, de-duplicated patterns
     int nMaps;

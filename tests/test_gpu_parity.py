@@ -216,3 +216,31 @@ def test_error_behaviour(pkg, mesh_dir):
         eng.run(7, 0.0, 1)  # unknown integrator
     with pytest.raises(pkg.DgbError):
         eng.set_option("no_such_option", 1)
+
+
+@pytest.mark.parametrize("name,order,v0", [("cube.msh", 3, (30.0, 10.0, 5.0)), ("sphere.msh", 4, (0, 0, 0)), ("cube:5", 4, (30.0, 10.0, 0.0)),
+                                           ("cube:3", 3, (0.0, 0.0, 0.0))])
+def test_tiled_dmma_kernel_vs_generic_and_oracle(pkg, oracle_mod, mesh_dir, name, order, v0):
+    """The FP64 tensor-core (DMMA) kernel and the CUDA-core kernel are two implementations of the same operator."""
+    mesh = build_mesh(pkg, mesh_dir, name, order, v0)
+    u = np.random.default_rng(5).standard_normal((4, mesh.N))
+    ref = oracle_mod.Oracle(mesh).eval_rhs(oracle_mod.Oracle.OPERATOR, u)
+    eng = pkg.Engine(mesh)
+    assert "tiled" in eng.kernel_name
+    tiled = eng.eval_rhs(u)
+    eng.set_option("kernel", 1)
+    assert "generic" in eng.kernel_name
+    generic = eng.eval_rhs(u)
+    for q in range(4):
+        assert rel_l2(tiled[q], ref[q]) < 1e-12
+        assert rel_l2(generic[q], ref[q]) < 1e-12
+    # and through a few RK4 steps with each kernel
+    u0 = smooth_state(mesh)
+    out = {}
+    for kern in (1, 2):
+        eng.set_option("kernel", kern)
+        eng.set_state(u0)
+        eng.run(pkg.RUNGE_KUTTA, 0.0, 5)
+        out[kern] = eng.get_state()
+    for q in range(4):
+        assert rel_l2(out[2][q], out[1][q]) < 1e-12
