@@ -64,4 +64,17 @@ __device__ __forceinline__ void rkUpdate(const StageArgs& A, int64_t g, double r
     }
 }
 
+// Same update with the RK registers already in hand (uval = u, or the stage input for Euler; accval = acc).
+__device__ __forceinline__ void rkApply(const StageArgs& A, int64_t g, double rhs, double uval, double accval) {
+    const double k = __dmul_rn(A.dt, rhs);
+    switch (A.mode) {
+        case MODE_RK1: A.acc[g] = k; A.yout[g] = uval + 0.5 * k; break;
+        case MODE_RK2: A.acc[g] = accval + 2 * k; A.yout[g] = uval + 0.5 * k; break;
+        case MODE_RK3: A.acc[g] = accval + 2 * k; A.yout[g] = uval + 1 * k; break;
+        case MODE_RK4: A.u[g] = uval + (accval + k) / 6.0; break;
+        case MODE_EULER: A.yout[g] = 1.0 * uval + k; break;
+        default: A.yout[g] = rhs; break;
+    }
+}
+
 }  // namespace dgb
