@@ -3,7 +3,7 @@
 * ``lib/libdgfront.so``  host front end (include/dgfront.h): MSH reader, config parser, Mesh set-up
 * ``lib/libdgb.so``      the CUDA engine (include/dgb.h) — the product; fails loudly without a GPU
 
-The CPU oracle is NOT reachable from here; its binding lives in ``oracle/oracle_py.py`` (test infrastructure).
+The CPU oracle is NOT reachable from here; its binding lives under ``oracle/`` (test infrastructure).
 
 Python is plumbing here: it never computes anything on the hot path.
 """
@@ -287,7 +287,7 @@ def load_dgb():
     if not path.exists():
         raise DgbError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first "
                        "(the CUDA engine has no CPU fallback)")
-    lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(str(path))
     lib.dgb_last_error.restype = C.c_char_p
     lib.dgb_version.restype = C.c_char_p
     lib.dgb_kernel_name.restype = C.c_char_p

@@ -1,5 +1,6 @@
 // C ABI of the engine (include/dgb.h): operator construction, upload, device-resident time loop, halo exchange.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -31,10 +32,48 @@ struct DgbException : std::runtime_error {
         if (_e != cudaSuccess)                                                                                   \
             throw DgbException(DGB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     } while (0)
+// NCCL is bound with dlopen the first time a partitioned handle (or a unique id) is requested: single-GPU users need
+// no NCCL at all, and a process that already carries an NCCL (e.g. the one bundled with PyTorch, same SONAME
+// libnccl.so.2) keeps using exactly that one instead of getting a second copy mapped over it.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.ok) return api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw DgbException(DGB_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+        void* p = dlsym(h, n);
+        if (!p) throw DgbException(DGB_ERR_NCCL, std::string("libnccl lacks ") + n);
+        return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = true;
+    return api;
+}
+
 #define NCCL_CHECK(expr)                                                                                         \
     do {                                                                                                         \
         ncclResult_t _r = (expr);                                                                                \
-        if (_r != ncclSuccess) throw DgbException(DGB_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(_r)); \
+        if (_r != ncclSuccess) throw DgbException(DGB_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(_r)); \
     } while (0)
 
 template <typename T>
@@ -116,7 +155,7 @@ void freeHandle(dgb_handle* h) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
-    if (h->comm) ncclCommDestroy(h->comm);
+    if (h->comm) nccl().CommDestroy(h->comm);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -388,7 +427,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
             CUDA_CHECK(cudaEventCreateWithFlags(&h->evRecv, cudaEventDisableTiming));
             ncclUniqueId id;
             std::memcpy(&id, ncclId, sizeof(id));
-            NCCL_CHECK(ncclCommInitRank(&h->comm, nranks, id, rank));
+            NCCL_CHECK(nccl().CommInitRank(&h->comm, nranks, id, rank));
             h->sendBuf = devAlloc<double>((size_t)4 * P.sendElems.size() * Np);
             h->dSendElems = devUpload(P.sendElems);
         }
@@ -418,19 +457,19 @@ void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
     const PartitionPlan& P = h->plan;
     const int Np = h->Np;
     const int64_t S = h->M.stride;
-    NCCL_CHECK(ncclGroupStart());
+    NCCL_CHECK(nccl().GroupStart());
     for (size_t i = 0; i < P.peers.size(); ++i) {
         const int peer = P.peers[i];
         const int nSend = P.sendOffset[i + 1] - P.sendOffset[i], nRecv = P.recvOffset[i + 1] - P.recvOffset[i];
         const int64_t totalSend = (int64_t)P.sendElems.size() * Np;
         for (int q = 0; q < 4; ++q) {
             if (nSend > 0)
-                NCCL_CHECK(ncclSend(h->sendBuf + q * totalSend + (int64_t)P.sendOffset[i] * Np, (size_t)nSend * Np, ncclDouble, peer, h->comm, s));
+                NCCL_CHECK(nccl().Send(h->sendBuf + q * totalSend + (int64_t)P.sendOffset[i] * Np, (size_t)nSend * Np, ncclDouble, peer, h->comm, s));
             if (nRecv > 0)
-                NCCL_CHECK(ncclRecv(y + q * S + (int64_t)(P.Kown + P.recvOffset[i]) * Np, (size_t)nRecv * Np, ncclDouble, peer, h->comm, s));
+                NCCL_CHECK(nccl().Recv(y + q * S + (int64_t)(P.Kown + P.recvOffset[i]) * Np, (size_t)nRecv * Np, ncclDouble, peer, h->comm, s));
         }
     }
-    NCCL_CHECK(ncclGroupEnd());
+    NCCL_CHECK(nccl().GroupEnd());
 }
 
 // One stage = [border elements -> pack -> exchange on the comm stream] overlapped with [interior elements].
@@ -600,7 +639,7 @@ int dgb_nccl_unique_id(void* out128) {
     return guarded([&] {
         if (!out128) throw DgbException(DGB_ERR_ARG, "out128 is null");
         ncclUniqueId id;
-        NCCL_CHECK(ncclGetUniqueId(&id));
+        NCCL_CHECK(nccl().GetUniqueId(&id));
         static_assert(sizeof(id) == 128, "ncclUniqueId is expected to be 128 bytes");
         std::memcpy(out128, &id, sizeof(id));
     });

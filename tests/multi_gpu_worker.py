@@ -1,0 +1,67 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (launched with torch.distributed.run).
+
+Every rank builds the same mesh, partitions it with RCB, runs RK4 through dgb_create_partitioned / dgb_run and
+writes the elements it owns; rank 0 also runs the single-GPU engine as the reference result.
+"""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as graft  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    out_dir, cells, order, steps, overlap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = graft.load_package()
+    model = pkg.Model.make_cube(cells, -10.0, 10.0, order)
+    cfg = pkg.Config()
+    cfg.add_initial_condition(1.0, -2.0, 0.5, 30.0, 1.0)
+    cfg.add_source(2.0, 1.0, 0.0, 6.0, 10.0, 1500.0, 0.0, 1.0)
+    mesh = pkg.Mesh(model, cfg)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * (2 * order + 1)))
+    b = np.nonzero(mesh.fIsBoundary)[0]
+    mesh.fBC[b[::3]] = 1
+    part = np.zeros(mesh.K, dtype=np.int32)
+    assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5), mesh.nearest_node(-7, 3, -2)], dtype=np.int32)
+    u0 = mesh.initial_condition()
+    eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes(), options={"overlap": overlap})
+    eng.set_sources_from_config()
+    eng.set_probes(probes)
+    eng.set_state(u0)
+    eng.run(pkg.RUNGE_KUTTA, 0.0, steps)
+    got = np.full((4, mesh.N), np.nan)
+    eng.get_state(got)
+    rec = eng.get_probes(steps)
+    owned = np.repeat(part == rank, mesh.Np)
+    np.savez(Path(out_dir) / f"rank{rank}.npz", u=got, owned=owned, probes=rec, launches=eng.launch_count)
+    eng.close()
+    if rank == 0:
+        single = pkg.Engine(mesh)
+        single.set_sources_from_config()
+        single.set_probes(probes)
+        single.set_state(u0)
+        single.run(pkg.RUNGE_KUTTA, 0.0, steps)
+        np.savez(Path(out_dir) / "single.npz", u=single.get_state(), probes=single.get_probes(steps))
+        single.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
