@@ -64,6 +64,20 @@ __device__ __forceinline__ void rkUpdate(const StageArgs& A, int64_t g, double r
     }
 }
 
+// Same update with k = dt*L(y) already formed (the tiled kernel folds dt into the operators) and the RK registers in
+// hand (uval = u, or the stage input for Euler; accval = acc). The final combine multiplies by 1/6 instead of dividing:
+// one FP64 instruction instead of a division sequence, <= 1 ulp away from the reference expression.
+__device__ __forceinline__ void rkApplyK(const StageArgs& A, int64_t g, double k, double uval, double accval) {
+    switch (A.mode) {
+        case MODE_RK1: A.acc[g] = k; A.yout[g] = fma(0.5, k, uval); break;
+        case MODE_RK2: A.acc[g] = fma(2.0, k, accval); A.yout[g] = fma(0.5, k, uval); break;
+        case MODE_RK3: A.acc[g] = fma(2.0, k, accval); A.yout[g] = uval + k; break;
+        case MODE_RK4: A.u[g] = fma(accval + k, 1.0 / 6.0, uval); break;
+        case MODE_EULER: A.yout[g] = uval + k; break;
+        default: A.yout[g] = k; break;
+    }
+}
+
 // Same update with the RK registers already in hand (uval = u, or the stage input for Euler; accval = acc).
 __device__ __forceinline__ void rkApply(const StageArgs& A, int64_t g, double rhs, double uval, double accval) {
     const double k = __dmul_rn(A.dt, rhs);

@@ -4,13 +4,21 @@
 //
 // Same fused operator as stage_generic.cu (updateFlux + numStep + RK axpys of the reference, Mesh.cpp:476-674,
 // solver.cpp:35-52, 261-285), organised as small dense contractions on mma.sync.m8n8k4.f64:
-//   T^u   = Dw^u  (NPP x NP)  x  Q  (NP x 8 columns)          columns = (element, field) pairs, 2 elements per n-tile
-//   rhs   = combine(T^u, G, v0)  -  LIFT (NPP x NFL) x Fl (NFL x 8 columns)
-// Persistent CTAs (one per SM); the operators (54 KB at p = 4) are staged once per CTA into shared memory with one
-// TMA bulk copy (cp.async.bulk + mbarrier); every WARP owns a unit of 4 consecutive elements end to end (load ->
-// neighbour gather / numerical flux -> DMMA contractions -> fused RK update straight from the accumulator
-// fragments), so warps only ever __syncwarp() and the memory phases of some warps overlap the tensor phases of
-// the others. All operand tiles are K-contiguous with a leading dimension chosen bank-conflict free (tile_cfg.h).
+//   lift  = -LIFT (NPP x NFL) x Fl (NFL x 8 columns)           columns = (element, field) pairs, 2 elements per n-tile
+//   T^u   =  Dw^u (NPP x NP)  x Q  (NP  x 8 columns)
+//   rhs   = combine(T^u, G, v0) + lift
+//
+// Structure (one persistent CTA per SM, 8 warps):
+//  * the operators (54 KB at p = 4) are staged once per CTA into shared memory with one TMA bulk copy
+//    (cp.async.bulk + mbarrier);
+//  * every WARP owns a unit of 4 consecutive elements end to end and only ever __syncwarp()s, so the memory phases of
+//    some warps overlap the tensor phases of the others;
+//  * software pipeline over units: while the DMMAs of unit k run, the nodal values, the neighbour traces (a gather
+//    through the face-node maps), the face geometry and the inverse Jacobians of unit k+1 stream into shared memory
+//    with cp.async (LDGSTS); the numerical flux of unit k+1 is then computed in place from shared memory;
+//  * the k = dt L(y) values go through shared memory once more so that the RK registers (u, acc, y) are read and written
+//    fully coalesced, with all loads of the unit in flight together.
+// All MMA operand tiles are K-contiguous with a leading dimension chosen bank-conflict free (tile_cfg.h).
 #include <algorithm>
 
 #include "dgb_device.cuh"
@@ -22,6 +30,7 @@ namespace dgb {
 namespace {
 
 constexpr int kMaxMaps = 64;
+constexpr int kWarps = 8;
 
 // Optional per-phase cycle counters (development aid): compile with -DDGB_TILED_PHASE_TIMERS, read with
 // dgbTiledPhaseTimers(). Off in the product build.
@@ -35,24 +44,40 @@ __device__ unsigned long long g_phase[8];
 #endif
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    // volatile: keeps the issue order written in the source, i.e. the accumulator chains stay interleaved (the DMMA
-    // pipe needs ~6 independent chains per warp to stay busy; ptxas otherwise groups the MMAs chain by chain)
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int P, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) stageTiledKernel(DeviceMesh M, StageArgs A, int nUnits) {
+// 8-byte asynchronous copy global -> shared (LDGSTS); valid == false writes zeros without touching global memory
+__device__ __forceinline__ void cpAsync8(void* dst, const void* src, bool valid) {
+    const int srcSize = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smemAddr(dst)), "l"(src), "r"(srcSize) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int P>
+struct WarpLayout {
     using T = TetTile<P>;
+    // per-warp staging (doubles): nodal values, two flux/trace buffers, inverse Jacobians and face geometry (x2)
+    static constexpr int Q = 16 * T::LDQ, FL = 16 * T::LDF, GEO = 4 * 9 + 16 * 4;
+    static constexpr int DOUBLES = Q + 2 * FL + 2 * GEO;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M, StageArgs A, int nUnits) {
+    using T = TetTile<P>;
+    using W = WarpLayout<P>;
     constexpr int NP = T::NP, NFP = T::NFP, NF = T::NF, NFL = T::NFL, MT = T::MT, NPP = T::NPP;
     constexpr int KTQ = T::KTQ, LDQ = T::LDQ, KTF = T::KTF, LDF = T::LDF;
+    constexpr int NIT = (4 * NFL + 31) / 32;  // flux tasks per lane
 
     extern __shared__ __align__(128) unsigned char smemRaw[];
     double* sD = reinterpret_cast<double*>(smemRaw);  // [3][NPP][LDQ]
     double* sL = sD + T::OPD;                         // [NPP][LDF]
     double* sWarpAll = sL + T::OPL;
-    int* sFaceNodes = reinterpret_cast<int*>(sWarpAll + WARPS * T::WARP_DOUBLES);
+    int* sFaceNodes = reinterpret_cast<int*>(sWarpAll + kWarps * W::DOUBLES);
     unsigned char* sMaps = reinterpret_cast<unsigned char*>(sFaceNodes + NFL);
     __shared__ __align__(8) unsigned long long bar;
 
@@ -72,12 +97,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) stageTiledKernel(DeviceMesh M, 
                      "l"(M.tiledOps), "r"(bytes), "r"(smemAddr(&bar))
                      : "memory");
     }
-    for (int i = tid; i < NFL; i += WARPS * 32) sFaceNodes[i] = M.faceNodes[i];
+    for (int i = tid; i < NFL; i += kWarps * 32) sFaceNodes[i] = M.faceNodes[i];
     const int nMapsS = min(M.nMaps, kMaxMaps);
-    for (int i = tid; i < nMapsS * NFP; i += WARPS * 32) sMaps[i] = M.nbrMaps[i];
-    double* sQ = sWarpAll + warp * T::WARP_DOUBLES;  // [16 columns][LDQ]
-    double* sFl = sQ + 16 * LDQ;                     // [16 columns][LDF]
-    for (int i = lane; i < T::WARP_DOUBLES; i += 32) sQ[i] = 0.0;  // padding entries stay zero for ever
+    for (int i = tid; i < nMapsS * NFP; i += kWarps * 32) sMaps[i] = M.nbrMaps[i];
+    double* sQ = sWarpAll + warp * W::DOUBLES;  // [16 columns][LDQ]
+    double* sFlBuf = sQ + W::Q;                 // 2 x [16 columns][LDF]
+    double* sGeoBuf = sFlBuf + 2 * W::FL;       // 2 x { Ginv [4][9], fgeo [16][4] }
+    for (int i = lane; i < W::DOUBLES; i += 32) sQ[i] = 0.0;  // the K padding of sQ stays zero for ever
     {
         uint32_t done = 0;
         while (!done) {
@@ -89,246 +115,336 @@ __global__ void __launch_bounds__(WARPS * 32, 1) stageTiledKernel(DeviceMesh M, 
         }
     }
     __syncthreads();
+    // k = dt * L(y) comes straight out of the contractions: the staged operators are scaled by dt once per CTA
+    // (dt == 1 for MODE_RHS), which removes one FP64 multiply per unknown from the FP64 pipe the DMMAs need.
+    {
+        const double dtScale = A.mode == MODE_RHS ? 1.0 : A.dt;
+        for (int i = tid; i < T::OPS; i += kWarps * 32) sD[i] *= dtScale;
+    }
+    __syncthreads();
 
     const Phys ph = makePhys(M);
     const int64_t S = M.stride;
-    const int fp = t & 1;        // field pair of this lane's two accumulator columns: (p,vx) or (vy,vz)
-    const int elSub = t >> 1;    // which of the n-tile's two elements
+    const int fp = t & 1;      // field pair of this lane's two accumulator columns: (p,vx) or (vy,vz)
+    const int elSub = t >> 1;  // which of the n-tile's two elements
+    const int unitStride = gridDim.x * kWarps;
+    const int mel = (lane & 15) >> 2, mlf = lane & 3;  // the face this lane looks after in the metadata step
 
-    for (int unit = blockIdx.x * WARPS + warp; unit < nUnits; unit += gridDim.x * WARPS) {
+    // Face metadata of a unit: lane (el*4+lf) holds flags / neighbour of its face (lanes 16..31 mirror 0..15).
+    auto loadFaceIds = [&](int unit, int& flags, int& nbr) {
+        flags = FACE_ABSORBING;
+        nbr = -1;
+        if (unit < nUnits) {
+            const int e = A.eBegin + unit * 4 + mel;
+            if (e < A.eEnd) { flags = M.fflags[e * NF + mlf]; nbr = M.fnbr[e * NF + mlf]; }
+        }
+    };
+    // Everything unit `unit` needs, streamed into shared memory: nodal values, neighbour traces, geometry.
+    auto prefetch = [&](int unit, int buf, int flags, int nbr) {
+        if (unit >= nUnits) return;
         const int e0 = A.eBegin + unit * 4;
         const int nE = min(4, A.eEnd - e0);
-
-        PHASE_T(tp0);
-        // ---- 1. nodal values of the unit's 4 elements: coalesced per field, stored column-major (K-contiguous) ----
+        double* sFl = sFlBuf + buf * W::FL;
+        double* sGeo = sGeoBuf + buf * W::GEO;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const double* src = A.yin + q * S + (int64_t)e0 * NP;
 #pragma unroll
             for (int idx = lane; idx < 4 * NP; idx += 32) {
                 const int el = idx / NP, j = idx - el * NP;
-                sQ[(el * 4 + q) * LDQ + j] = el < nE ? src[idx] : 0.0;
+                cpAsync8(&sQ[(el * 4 + q) * LDQ + j], el < nE ? src + idx : A.yin, el < nE);
             }
         }
-        __syncwarp();
-
-        PHASE_T(tp1);
-        PHASE_ADD(0, tp0, tp1);
-        // ---- 2. numerical flux at every (element, face, face node) ----
-        // 2a. face metadata: lane (el*4+lf) loads its face once and pre-multiplies the flux coefficients; the task
-        //     lanes fetch them with shuffles (keeps the scarce FP64 pipe for the contractions).
-        constexpr int NIT = (4 * NFL + 31) / 32;
-        int mflags = FACE_ABSORBING, mnbr = -1;
-        double mn0 = 0, mn1 = 0, mn2 = 0, mfs = 0;
-        {
-            const int mel = (lane & 15) >> 2, mlf = lane & 3;
-            if (mel < nE) {
-                const int e = e0 + mel;
-                mflags = M.fflags[e * NF + mlf];
-                mnbr = M.fnbr[e * NF + mlf];
-                const double4 fg = *reinterpret_cast<const double4*>(M.fgeo + ((int64_t)e * NF + mlf) * 4);
-                mn0 = fg.x; mn1 = fg.y; mn2 = fg.z; mfs = fg.w;
-            }
-        }
-        // per-lane geometric factors of the two elements this lane's columns belong to (one per n-tile); issued here
-        // so that their latency overlaps the gathers
-        double G[2][9];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const int el = nt * 2 + elSub;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) G[nt][k] = el < nE ? M.Ginv[(int64_t)(e0 + el) * 9 + k] : 0.0;
-        }
-        const double mhf = 0.5 * mfs;
-        const double cA = mhf * (ph.v0[0] * mn0 + ph.v0[1] * mn1 + ph.v0[2] * mn2);       // 1/2 Fscale v0.n
-        const double cB = mhf * ph.rc2;                                                    // 1/2 Fscale rho0 c0^2
-        const double cP = ((mflags & FLAG_TAU_NEG) ? -mhf : mhf) * ph.c0;                  // 1/2 Fscale tau c0
-        const double cN0 = mhf * ph.invRho * mn0, cN1 = mhf * ph.invRho * mn1, cN2 = mhf * ph.invRho * mn2;
-        // 2b. all neighbour gathers of the unit in flight at once
-        double qp[NIT][4];
-        int tflags[NIT];
 #pragma unroll
         for (int s2 = 0; s2 < NIT; ++s2) {
             const int w = s2 * 32 + lane;
             const int el = min(w / NFL, 3), r = w - (w / NFL) * NFL, lf = r / NFP, m = r - lf * NFP;
             const int src = el * 4 + lf;
-            const int flags = __shfl_sync(0xffffffffu, mflags, src);
-            const int nb = __shfl_sync(0xffffffffu, mnbr, src);
-            tflags[s2] = flags;
-            const bool interior = (w < 4 * NFL) && ((flags & FLAG_BC_MASK) == FACE_INTERIOR) && nb >= 0;
-            const int mapId = flags >> FLAG_MAP_SHIFT;
-            int nn = 0;
-            if (interior) nn = mapId < kMaxMaps ? sMaps[mapId * NFP + m] : M.nbrMaps[mapId * NFP + m];
-            const int64_t gi = (int64_t)nb * NP + nn;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) qp[s2][q] = interior ? A.yin[q * S + gi] : 0.0;
-        }
-        PHASE_T(tp2);
-        PHASE_ADD(1, tp1, tp2);
-        // 2c. fluxes (Fscale and the 1/2 are folded into the shuffled coefficients)
-#pragma unroll
-        for (int s2 = 0; s2 < NIT; ++s2) {
-            const int w = s2 * 32 + lane;
-            const int el = min(w / NFL, 3), r = w - (w / NFL) * NFL, lf = r / NFP;
-            const int src = el * 4 + lf;
-            const double n0 = __shfl_sync(0xffffffffu, mn0, src), n1 = __shfl_sync(0xffffffffu, mn1, src), n2 = __shfl_sync(0xffffffffu, mn2, src);
-            const double fs = __shfl_sync(0xffffffffu, mfs, src);
-            const double a = __shfl_sync(0xffffffffu, cA, src), b = __shfl_sync(0xffffffffu, cB, src), pc = __shfl_sync(0xffffffffu, cP, src);
-            const double d0 = __shfl_sync(0xffffffffu, cN0, src), d1 = __shfl_sync(0xffffffffu, cN1, src), d2 = __shfl_sync(0xffffffffu, cN2, src);
+            const int fl = __shfl_sync(0xffffffffu, flags, src);
+            const int nb = __shfl_sync(0xffffffffu, nbr, src);
             if (w < 4 * NFL) {
-                const int own = sFaceNodes[r];
-                double qm[4], fl[4];
+                const bool interior = ((fl & FLAG_BC_MASK) == FACE_INTERIOR) && nb >= 0;
+                const int mapId = fl >> FLAG_MAP_SHIFT;
+                int nn = 0;
+                if (interior) nn = mapId < kMaxMaps ? sMaps[mapId * NFP + m] : M.nbrMaps[mapId * NFP + m];
+                const int64_t gi = interior ? (int64_t)nb * NP + nn : 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) qm[q] = sQ[(el * 4 + q) * LDQ + own];
-                const int bc = tflags[s2] & FLAG_BC_MASK;
+                for (int q = 0; q < 4; ++q) cpAsync8(&sFl[(el * 4 + q) * LDF + r], A.yin + q * S + gi, interior);
+            }
+        }
+        for (int i = lane; i < 36; i += 32) cpAsync8(&sGeo[i], i < nE * 9 ? M.Ginv + (int64_t)e0 * 9 + i : M.Ginv, i < nE * 9);
+        for (int i = lane; i < 64; i += 32) cpAsync8(&sGeo[36 + i], i < nE * 16 ? M.fgeo + (int64_t)e0 * 16 + i : M.fgeo, i < nE * 16);
+    };
+
+    int unit = blockIdx.x * kWarps + warp;
+    int flagsCur, nbrCur, flagsNext = FACE_ABSORBING, nbrNext = -1;
+    loadFaceIds(unit, flagsCur, nbrCur);
+    prefetch(unit, 0, flagsCur, nbrCur);
+    cpAsyncCommit();
+
+    for (int iter = 0; unit < nUnits; unit += unitStride, ++iter) {
+        const int buf = iter & 1;
+        const int e0 = A.eBegin + unit * 4;
+        const int nE = min(4, A.eEnd - e0);
+        double* sFl = sFlBuf + buf * W::FL;
+        const double* sGeo = sGeoBuf + buf * W::GEO;
+        PHASE_T(tp0);
+        loadFaceIds(unit + unitStride, flagsNext, nbrNext);  // consumed by the prefetch below, after the flux phase
+        cpAsyncWaitAll();
+        __syncwarp();
+        PHASE_T(tp1);
+        PHASE_ADD(0, tp0, tp1);
+
+        // ---- 1. numerical flux at every (element, face, face node), in place over the gathered neighbour traces ----
+        // Two lanes per face (lane & 15 = el*4+lf; lane >> 4 picks the even / odd face nodes): every coefficient of the
+        // face is lane-local, no shuffles; Fscale and the 1/2 of the central flux are folded into the coefficients.
+        {
+            const double* fg = sGeo + 36 + (mel * 4 + mlf) * 4;
+            const double n0 = fg[0], n1 = fg[1], n2 = fg[2], fs = fg[3];
+            const double hf = 0.5 * fs;
+            const double cA = hf * (ph.v0[0] * n0 + ph.v0[1] * n1 + ph.v0[2] * n2);  // 1/2 Fscale v0.n
+            const double cP = ((flagsCur & FLAG_TAU_NEG) ? -hf : hf) * ph.c0;         // 1/2 Fscale tau c0
+            const double cm = cA + cP, cp = cA - cP;                                  // weights of the own / neighbour value
+            const double cB = hf * ph.rc2, cR = hf * ph.invRho;
+            const double g0 = cB * n0, g1 = cB * n1, g2 = cB * n2;                    // 1/2 Fscale rho0 c0^2 n
+            const double d0 = cR * n0, d1 = cR * n1, d2 = cR * n2;                    // 1/2 Fscale n / rho0
+            const int bc = flagsCur & FLAG_BC_MASK;
+            const double* qBase = sQ + mel * 4 * LDQ;
+            double* fBase = sFl + mel * 4 * LDF + mlf * NFP;
+            const int* fn = sFaceNodes + mlf * NFP;
+#pragma unroll 4
+            for (int m = lane >> 4; m < NFP; m += 2) {
+                const int own = fn[m];
+                double qm[4], qp[4], fl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { qm[q] = qBase[q * LDQ + own]; qp[q] = fBase[q * LDF + m]; }
                 if (bc == FACE_INTERIOR) {
-                    const double ps = qm[0] + qp[s2][0], v0s = qm[1] + qp[s2][1], v1s = qm[2] + qp[s2][2], v2s = qm[3] + qp[s2][3];
-                    const double vns = n0 * v0s + n1 * v1s + n2 * v2s;
-                    fl[0] = a * ps + b * vns + pc * (qm[0] - qp[s2][0]);
-                    fl[1] = a * v0s + d0 * ps + pc * (qm[1] - qp[s2][1]);
-                    fl[2] = a * v1s + d1 * ps + pc * (qm[2] - qp[s2][2]);
-                    fl[3] = a * v2s + d2 * ps + pc * (qm[3] - qp[s2][3]);
+                    const double ps = qm[0] + qp[0];
+                    fl[0] = cm * qm[0] + cp * qp[0] + g0 * (qm[1] + qp[1]) + g1 * (qm[2] + qp[2]) + g2 * (qm[3] + qp[3]);
+                    fl[1] = cm * qm[1] + cp * qp[1] + d0 * ps;
+                    fl[2] = cm * qm[2] + cp * qp[2] + d1 * ps;
+                    fl[3] = cm * qm[3] + cp * qp[3] + d2 * ps;
                 } else {
                     const double n[3] = {n0, n1, n2};
-                    faceFlux(bc, 1.0, n, ph, qm, qp[s2], fl);
+                    faceFlux(bc, 1.0, n, ph, qm, qp, fl);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) fl[q] *= fs;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sFl[(el * 4 + q) * LDF + r] = fl[q];
+                for (int q = 0; q < 4; ++q) fBase[q * LDF + m] = fl[q];
             }
         }
         __syncwarp();
+        PHASE_T(tp2);
+        PHASE_ADD(1, tp1, tp2);
 
-        PHASE_T(tp3);
-        PHASE_ADD(2, tp2, tp3);
-        // ---- 3. B fragments of the volume contraction (reused by all 3*MT m-tiles) ----
+        // ---- 2. B fragments of the volume contraction, then release sQ to the prefetch of the next unit ----
         double Bq[2][KTQ];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int kt = 0; kt < KTQ; ++kt) Bq[nt][kt] = sQ[(nt * 8 + g) * LDQ + 4 * kt + t];
+        __syncwarp();
+        prefetch(unit + unitStride, buf ^ 1, flagsNext, nbrNext);
+        cpAsyncCommit();
+        PHASE_T(tp3);
+        PHASE_ADD(2, tp2, tp3);
 
-#pragma unroll 1
-        for (int it = 0; it < MT; ++it) {
-            // RK registers of this m-tile's rows: requested now, consumed after the tile's MMAs
-            const int i = it * 8 + g;
-            const bool rowOk = i < NP;
-            int64_t gIdx[2];
-            double uPre[2][2], accPre[2][2];
+        // ---- 3. lift for all m-tiles: R[it] = -LIFT (Fscale * flux); operand fragments are fetched one k-step ahead ----
+        {
+            double R[MT][2][2];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const int el = nt * 2 + elSub;
-                gIdx[nt] = (int64_t)(fp * 2) * S + (int64_t)(e0 + el) * NP + i;
-                const bool ok = rowOk && el < nE;
+            for (int it = 0; it < MT; ++it)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int64_t gi = gIdx[nt] + c * S;
-                    uPre[nt][c] = (ok && A.mode != MODE_RHS) ? (A.mode == MODE_EULER ? A.yin[gi] : A.u[gi]) : 0.0;
-                    accPre[nt][c] = (ok && A.mode >= MODE_RK2 && A.mode <= MODE_RK4) ? A.acc[gi] : 0.0;
+                for (int nt = 0; nt < 2; ++nt) R[it][nt][0] = R[it][nt][1] = 0.0;
+            const double* lRow = sL + g * LDF + t;
+            const double* fRow0 = sFl + g * LDF + t;
+            const double* fRow1 = sFl + (8 + g) * LDF + t;
+            double aN[MT], b0N = fRow0[0], b1N = fRow1[0];
+#pragma unroll
+            for (int it = 0; it < MT; ++it) aN[it] = lRow[it * 8 * LDF];
+#pragma unroll
+            for (int kt = 0; kt < KTF; ++kt) {
+                double a[MT];
+                const double b0 = b0N, b1 = b1N;
+#pragma unroll
+                for (int it = 0; it < MT; ++it) a[it] = aN[it];
+                if (kt + 1 < KTF) {
+                    b0N = fRow0[4 * (kt + 1)];
+                    b1N = fRow1[4 * (kt + 1)];
+#pragma unroll
+                    for (int it = 0; it < MT; ++it) aN[it] = lRow[it * 8 * LDF + 4 * (kt + 1)];
+                }
+#pragma unroll
+                for (int it = 0; it < MT; ++it) {
+                    dmma884(R[it][0][0], R[it][0][1], a[it], b0);
+                    dmma884(R[it][1][0], R[it][1][1], a[it], b1);
                 }
             }
-            // ---- 3a. T^u = Dw^u Q for the 8 rows of this m-tile ----
-            double Tacc[3][2][2];
+            __syncwarp();  // every lane is done reading the fluxes: sFl becomes the output staging area
+#pragma unroll
+            for (int it = 0; it < MT; ++it) {
+                const int i = it * 8 + g;
+                if (i < NP) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int col = (nt * 2 + elSub) * 4 + fp * 2;
+                        sFl[col * LDF + i] = R[it][nt][0];
+                        sFl[(col + 1) * LDF + i] = R[it][nt][1];
+                    }
+                }
+            }
+        }
+        PHASE_T(tp4);
+        PHASE_ADD(3, tp3, tp4);
+
+        // ---- 4. volume term per m-tile, combined with the per-element constants and added to the staged lift ----
+        // Branch-free combine: the coefficient set of a lane depends on whether its two columns are (p,vx) or (vy,vz).
+        //   own0 += cf0*Ta + cf1*Tb ; own1 += cf0*Tb + cf2*Ta ; send0 += cf3*Ta + cf4*Tb ; send1 += cf5*Ta
+        double cf[2][3][6];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const double* Gm = sGeo + (nt * 2 + elSub) * 9;  // Gm[x*3+u] = du_u/dx_x
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                cf[nt][u][0] = Gm[u] * ph.v0[0] + Gm[3 + u] * ph.v0[1] + Gm[6 + u] * ph.v0[2];
+                cf[nt][u][1] = fp == 0 ? ph.rc2 * Gm[u] : 0.0;
+                cf[nt][u][2] = fp == 0 ? ph.invRho * Gm[u] : 0.0;
+                cf[nt][u][3] = fp == 0 ? ph.invRho * Gm[3 + u] : ph.rc2 * Gm[3 + u];
+                cf[nt][u][4] = fp == 0 ? 0.0 : ph.rc2 * Gm[6 + u];
+                cf[nt][u][5] = fp == 0 ? ph.invRho * Gm[6 + u] : 0.0;
+            }
+        }
+        auto volumeMma = [&](int it, double (&Tacc)[3][2][2]) {
 #pragma unroll
             for (int u = 0; u < 3; ++u)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) Tacc[u][nt][0] = Tacc[u][nt][1] = 0.0;
             const double* aRow = sD + (it * 8 + g) * LDQ + t;
+            double aN[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ];
 #pragma unroll
             for (int kt = 0; kt < KTQ; ++kt) {
+                double a[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) a[u] = aN[u];
+                if (kt + 1 < KTQ) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ + 4 * (kt + 1)];
+                }
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
-                    const double a = aRow[u * NPP * LDQ + 4 * kt];
-                    dmma884(Tacc[u][0][0], Tacc[u][0][1], a, Bq[0][kt]);
-                    dmma884(Tacc[u][1][0], Tacc[u][1][1], a, Bq[1][kt]);
+                    dmma884(Tacc[u][0][0], Tacc[u][0][1], a[u], Bq[0][kt]);
+                    dmma884(Tacc[u][1][0], Tacc[u][1][1], a[u], Bq[1][kt]);
                 }
             }
-            // ---- 3b. combine with the per-element constants: rhs_vol (same fragment layout as the lift accumulators) ----
-            double R[2][2], R2[2][2], R3[2][2];
+        };
+        auto combine = [&](int it, const double (&Tacc)[3][2][2]) {
+            const int i = it * 8 + g;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const double* Gm = G[nt];  // Gm[x*3+u]
-                double au[3];
-#pragma unroll
-                for (int u = 0; u < 3; ++u) au[u] = Gm[u] * ph.v0[0] + Gm[3 + u] * ph.v0[1] + Gm[6 + u] * ph.v0[2];
-                double ownA = 0.0, ownB = 0.0, send0 = 0.0, send1 = 0.0;
+                double own0 = 0.0, own1 = 0.0, send0 = 0.0, send1 = 0.0;
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
                     const double Ta = Tacc[u][nt][0], Tb = Tacc[u][nt][1];
-                    ownA = fma(au[u], Ta, ownA);
-                    ownB = fma(au[u], Tb, ownB);
-                    if (fp == 0) {  // columns (p, vx)
-                        ownA = fma(ph.rc2 * Gm[u], Tb, ownA);
-                        ownB = fma(ph.invRho * Gm[u], Ta, ownB);
-                        send0 = fma(ph.invRho * Gm[3 + u], Ta, send0);
-                        send1 = fma(ph.invRho * Gm[6 + u], Ta, send1);
-                    } else {  // columns (vy, vz)
-                        send0 = fma(ph.rc2 * Gm[3 + u], Ta, send0);
-                        send0 = fma(ph.rc2 * Gm[6 + u], Tb, send0);
-                    }
+                    const double* c = cf[nt][u];
+                    own0 = fma(c[0], Ta, own0);
+                    own0 = fma(c[1], Tb, own0);
+                    own1 = fma(c[0], Tb, own1);
+                    own1 = fma(c[2], Ta, own1);
+                    send0 = fma(c[3], Ta, send0);
+                    send0 = fma(c[4], Tb, send0);
+                    send1 = fma(c[5], Ta, send1);
                 }
                 const double recv0 = __shfl_xor_sync(0xffffffffu, send0, 1);
                 const double recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-                R[nt][0] = ownA + recv0;
-                R[nt][1] = fp == 0 ? ownB : ownB + recv1;
-                R2[nt][0] = R2[nt][1] = R3[nt][0] = R3[nt][1] = 0.0;
-            }
-            // ---- 3c. lift: rhs -= LIFT (Fscale * flux), three accumulator chains per n-tile ----
-            const double* lRow = sL + (it * 8 + g) * LDF + t;
-            const double* fRow0 = sFl + g * LDF + t;
-            const double* fRow1 = sFl + (8 + g) * LDF + t;
-#pragma unroll
-            for (int kt = 0; kt < KTF; kt += 3) {
-                const double a0 = lRow[4 * kt];
-                dmma884(R[0][0], R[0][1], a0, fRow0[4 * kt]);
-                dmma884(R[1][0], R[1][1], a0, fRow1[4 * kt]);
-                if (kt + 1 < KTF) {
-                    const double a1 = lRow[4 * kt + 4];
-                    dmma884(R2[0][0], R2[0][1], a1, fRow0[4 * kt + 4]);
-                    dmma884(R2[1][0], R2[1][1], a1, fRow1[4 * kt + 4]);
-                }
-                if (kt + 2 < KTF) {
-                    const double a2 = lRow[4 * kt + 8];
-                    dmma884(R3[0][0], R3[0][1], a2, fRow0[4 * kt + 8]);
-                    dmma884(R3[1][0], R3[1][1], a2, fRow1[4 * kt + 8]);
+                // (p,vx) lanes: p += partner's divergence part, vx complete; (vy,vz) lanes: each gets its pressure-gradient part
+                if (i < NP) {
+                    const int col = (nt * 2 + elSub) * 4 + fp * 2;
+                    sFl[col * LDF + i] += own0 + recv0;
+                    sFl[(col + 1) * LDF + i] += fp == 0 ? own1 : own1 + recv1;
                 }
             }
-            // ---- 3d. fused RK update straight from the fragments (8 consecutive nodes per (element, field) = 64 B runs) ----
-            if (rowOk) {
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    if (nt * 2 + elSub < nE) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) rkApply(A, gIdx[nt] + c * S, (R[nt][c] + R2[nt][c]) + R3[nt][c], uPre[nt][c], accPre[nt][c]);
-                    }
-                }
+        };
+        {
+            double Ta0[3][2][2], Ta1[3][2][2];
+            volumeMma(0, Ta0);
+#pragma unroll 1
+            for (int it = 1; it + 1 < MT; it += 2) {  // two tiles per trip so that the two accumulator sets keep their names
+                volumeMma(it, Ta1);
+                combine(it - 1, Ta0);
+                volumeMma(it + 1, Ta0);
+                combine(it, Ta1);
+            }
+            if ((MT & 1) == 0) {
+                volumeMma(MT - 1, Ta1);
+                combine(MT - 2, Ta0);
+                combine(MT - 1, Ta1);
+            } else {
+                combine(MT - 1, Ta0);
             }
         }
-        __syncwarp();  // the next unit overwrites this warp's staging area
-        PHASE_T(tp4);
-        PHASE_ADD(3, tp3, tp4);
+        __syncwarp();
+        PHASE_T(tp5);
+        PHASE_ADD(4, tp4, tp5);
+
+        // ---- 5. fused RK update, coalesced: all RK-register loads of the unit in flight, then the stores ----
+        {
+            constexpr int NV = (4 * NP + 31) / 32;
+            const int nValid = nE * NP;
+            double uv[4][NV], av[4][NV];
+            const bool needU = A.mode != MODE_RHS;
+            const bool needAcc = A.mode >= MODE_RK2 && A.mode <= MODE_RK4;
+            const double* uSrc = A.mode == MODE_EULER ? A.yin : A.u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int s2 = 0; s2 < NV; ++s2) {
+                    const int idx = s2 * 32 + lane;
+                    const int64_t gi = q * S + (int64_t)e0 * NP + idx;
+                    const bool ok = idx < nValid;
+                    uv[q][s2] = (ok && needU) ? uSrc[gi] : 0.0;
+                    av[q][s2] = (ok && needAcc) ? A.acc[gi] : 0.0;
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int s2 = 0; s2 < NV; ++s2) {
+                    const int idx = s2 * 32 + lane;
+                    if (idx < nValid) {
+                        const int el = idx / NP, i = idx - el * NP;
+                        rkApplyK(A, q * S + (int64_t)e0 * NP + idx, sFl[(el * 4 + q) * LDF + i], uv[q][s2], av[q][s2]);
+                    }
+                }
+        }
+        __syncwarp();
+        PHASE_T(tp6);
+        PHASE_ADD(5, tp5, tp6);
+        flagsCur = flagsNext;
+        nbrCur = nbrNext;
     }
+    cpAsyncWaitAll();
 }
 
-template <int P, int WARPS>
+template <int P>
 void launchTiled(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using T = TetTile<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
     static int numSm = 0;
     static bool configured = false;
-    const size_t smem = (size_t)(T::OPS + WARPS * T::WARP_DOUBLES) * sizeof(double) + T::NFL * sizeof(int) + kMaxMaps * T::NFP;
+    const size_t smem = (size_t)(T::OPS + kWarps * WarpLayout<P>::DOUBLES) * sizeof(double) + T::NFL * sizeof(int) + kMaxMaps * T::NFP;
     if (!configured) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(stageTiledKernel<P, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(stageTiledKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     const int nUnits = (nEl + 3) / 4;
-    const int grid = std::max(1, std::min(numSm, (nUnits + WARPS - 1) / WARPS));
-    stageTiledKernel<P, WARPS><<<grid, WARPS * 32, smem, s>>>(M, A, nUnits);
+    const int grid = std::max(1, std::min(numSm, (nUnits + kWarps - 1) / kWarps));
+    stageTiledKernel<P><<<grid, kWarps * 32, smem, s>>>(M, A, nUnits);
 }
 
 }  // namespace
@@ -342,8 +458,8 @@ extern "C" void dgbTiledPhaseTimers(unsigned long long* out, int reset) {
 
 StageKernel selectTiledKernel(int dim, int order) {
     StageKernel k;
-    if (dim == 3 && order == 4) { k.launch = &launchTiled<4, 12>; k.name = "stage_tiled_dmma<3,4>"; }
-    if (dim == 3 && order == 3) { k.launch = &launchTiled<3, 12>; k.name = "stage_tiled_dmma<3,3>"; }
+    if (dim == 3 && order == 4) { k.launch = &launchTiled<4>; k.name = "stage_tiled_dmma<3,4>"; }
+    if (dim == 3 && order == 3) { k.launch = &launchTiled<3>; k.name = "stage_tiled_dmma<3,3>"; }
     return k;
 }
 

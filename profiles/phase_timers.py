@@ -20,8 +20,8 @@ try:
     lib.dgbTiledPhaseTimers(buf, 1)
     t = np.array(list(buf), dtype=np.float64)
     nunits = mesh.K / 4 * 20
-    names = ["Q load", "metadata+gather issue", "flux compute", "Bq+MMA+epilogue"]
+    names = ["wait prefetch", "flux compute", "Bq/G + issue prefetch", "lift MMA", "volume MMA + combine", "RK epilogue"]
     print("cells", cells, "stage ms", eng.last_stage_kernel_ms, "kernel", eng.kernel_name)
-    for n, v in zip(names, t[:4]): print(f"{n:26s} {v / nunits:10.0f} cycles per unit per warp ({100 * v / t[:4].sum():.1f}%)")
+    for n, v in zip(names, t[:6]): print(f"{n:26s} {v / nunits:10.0f} cycles per unit per warp ({100 * v / t[:6].sum():.1f}%)")
 finally:
     shutil.copy(bak, orig); os.remove(bak)

@@ -1,0 +1,15 @@
+"""Small RK4 run through the tiled kernel for compute-sanitizer (memcheck / racecheck)."""
+import sys
+import numpy as np
+sys.path.insert(0, "/root/repo")
+import __graft_entry__ as g
+pkg = g.load_package()
+order = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+mesh = pkg.Mesh(pkg.Model.make_cube(3, -10.0, 10.0, order), pkg.Config())
+mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0), dt=1e-5)
+b = np.nonzero(mesh.fIsBoundary)[0]; mesh.fBC[b[::2]] = 1
+eng = pkg.Engine(mesh)
+eng.set_state(np.random.default_rng(0).standard_normal((4, mesh.N)))
+eng.run(pkg.RUNGE_KUTTA, 0.0, 2)
+eng.run(pkg.EULER1, 0.0, 1)
+print(eng.kernel_name, float(np.abs(eng.get_state()).max()))
