@@ -145,7 +145,7 @@ struct dgb_handle {
     ncclComm_t comm = nullptr;
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int32_t* dSendElems = nullptr;
-    std::vector<double> hostStage;
+    double* hostStage = nullptr;  // pinned, [4][stride], partitioned handles only
 };
 
 namespace {
@@ -156,6 +156,7 @@ void freeHandle(dgb_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
     if (h->comm) nccl().CommDestroy(h->comm);
+    if (h->hostStage) cudaFreeHost(h->hostStage);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -575,6 +576,11 @@ int guarded(Fn fn) {
 }
 
 // host <-> device state transfer; identity layout on one GPU, gather/scatter by element when partitioned
+double* stagingBuffer(dgb_handle* h) {
+    if (!h->hostStage) CUDA_CHECK(cudaMallocHost(&h->hostStage, (size_t)4 * h->M.stride * sizeof(double)));
+    return h->hostStage;
+}
+
 void stateToDevice(dgb_handle* h, const double* u, double* dst) {
     const int Np = h->Np;
     const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
@@ -583,11 +589,14 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         return;
     }
-    h->hostStage.resize((size_t)4 * S);
+    double* stage = stagingBuffer(h);
+    const int32_t* l2g = h->plan.localToGlobal.data();
+    const int Ktot = h->M.Ktot;
+#pragma omp parallel for collapse(2) schedule(static)
     for (int q = 0; q < 4; ++q)
-        for (int l = 0; l < h->M.Ktot; ++l)
-            std::memcpy(&h->hostStage[(size_t)q * S + (size_t)l * Np], u + q * Ng + (int64_t)h->plan.localToGlobal[l] * Np, Np * sizeof(double));
-    CUDA_CHECK(cudaMemcpyAsync(dst, h->hostStage.data(), (size_t)4 * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        for (int l = 0; l < Ktot; ++l)
+            std::memcpy(stage + (size_t)q * S + (size_t)l * Np, u + q * Ng + (int64_t)l2g[l] * Np, Np * sizeof(double));
+    CUDA_CHECK(cudaMemcpyAsync(dst, stage, (size_t)4 * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
@@ -599,12 +608,15 @@ void stateToHost(dgb_handle* h, const double* src, double* u) {
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         return;
     }
-    h->hostStage.resize((size_t)4 * S);
-    CUDA_CHECK(cudaMemcpyAsync(h->hostStage.data(), src, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double* stage = stagingBuffer(h);
+    CUDA_CHECK(cudaMemcpyAsync(stage, src, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    const int32_t* l2g = h->plan.localToGlobal.data();
+    const int Kown = h->M.Kown;
+#pragma omp parallel for collapse(2) schedule(static)
     for (int q = 0; q < 4; ++q)
-        for (int l = 0; l < h->M.Kown; ++l)  // owned elements only
-            std::memcpy(u + q * Ng + (int64_t)h->plan.localToGlobal[l] * Np, &h->hostStage[(size_t)q * S + (size_t)l * Np], Np * sizeof(double));
+        for (int l = 0; l < Kown; ++l)  // owned elements only
+            std::memcpy(u + q * Ng + (int64_t)l2g[l] * Np, stage + (size_t)q * S + (size_t)l * Np, Np * sizeof(double));
 }
 
 // global DG node index -> local (or -1); halo copies included when withHalo
