@@ -61,17 +61,24 @@ template <int P>
 struct WarpLayout {
     using T = TetTile<P>;
     // per-warp staging (doubles): nodal values, two flux/trace buffers, inverse Jacobians and face geometry (x2)
-    static constexpr int Q = 16 * T::LDQ, FL = 16 * T::LDF, GEO = 4 * 9 + 16 * 4;
+    // 16 columns of (element, field); 4 extra doubles after every element's 4 columns, so that the four elements of a
+    // unit start in different bank groups (the flux phase works with one lane pair per (element, face))
+    static constexpr int Q = 16 * T::LDQ + 16, FL = 16 * T::LDF + 16, GEO = 4 * 9 + 16 * 4;
     static constexpr int DOUBLES = Q + 2 * FL + 2 * GEO;
 };
 
-template <int P>
+// FLOW == false is the v0 == 0 specialisation: the velocity columns are pre-combined with the inverse Jacobian
+// (c_u = sum_x G_xu v_x, in place in shared memory), so operator Dw^u only has to see the 8 columns
+// (p of 4 elements | c_u of 4 elements): 135 instead of 270 volume MMAs per unit and no cross-lane exchange.
+template <int P, bool FLOW>
 __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M, StageArgs A, int nUnits) {
     using T = TetTile<P>;
     using W = WarpLayout<P>;
     constexpr int NP = T::NP, NFP = T::NFP, NF = T::NF, NFL = T::NFL, MT = T::MT, NPP = T::NPP;
     constexpr int KTQ = T::KTQ, LDQ = T::LDQ, KTF = T::KTF, LDF = T::LDF;
     constexpr int NIT = (4 * NFL + 31) / 32;  // flux tasks per lane
+    auto colQ = [](int c) { return c * LDQ + (c >> 2) * 4; };  // start of column c = (element*4 + field) in sQ
+    auto colF = [](int c) { return c * LDF + (c >> 2) * 4; };  // ... and in the flux / staging buffers
 
     extern __shared__ __align__(128) unsigned char smemRaw[];
     double* sD = reinterpret_cast<double*>(smemRaw);  // [3][NPP][LDQ]
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
 #pragma unroll
             for (int idx = lane; idx < 4 * NP; idx += 32) {
                 const int el = idx / NP, j = idx - el * NP;
-                cpAsync8(&sQ[(el * 4 + q) * LDQ + j], el < nE ? src + idx : A.yin, el < nE);
+                cpAsync8(&sQ[colQ(el * 4 + q) + j], el < nE ? src + idx : A.yin, el < nE);
             }
         }
 #pragma unroll
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
                 if (interior) nn = mapId < kMaxMaps ? sMaps[mapId * NFP + m] : M.nbrMaps[mapId * NFP + m];
                 const int64_t gi = interior ? (int64_t)nb * NP + nn : 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) cpAsync8(&sFl[(el * 4 + q) * LDF + r], A.yin + q * S + gi, interior);
+                for (int q = 0; q < 4; ++q) cpAsync8(&sFl[colF(el * 4 + q) + r], A.yin + q * S + gi, interior);
             }
         }
         for (int i = lane; i < 36; i += 32) cpAsync8(&sGeo[i], i < nE * 9 ? M.Ginv + (int64_t)e0 * 9 + i : M.Ginv, i < nE * 9);
@@ -209,29 +216,39 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
             const double g0 = cB * n0, g1 = cB * n1, g2 = cB * n2;                    // 1/2 Fscale rho0 c0^2 n
             const double d0 = cR * n0, d1 = cR * n1, d2 = cR * n2;                    // 1/2 Fscale n / rho0
             const int bc = flagsCur & FLAG_BC_MASK;
-            const double* qBase = sQ + mel * 4 * LDQ;
-            double* fBase = sFl + mel * 4 * LDF + mlf * NFP;
+            const double* qBase = sQ + colQ(mel * 4);
+            double* fBase = sFl + colF(mel * 4) + mlf * NFP;
             const int* fn = sFaceNodes + mlf * NFP;
-#pragma unroll 4
-            for (int m = lane >> 4; m < NFP; m += 2) {
-                const int own = fn[m];
-                double qm[4], qp[4], fl[4];
+            // all face nodes of the lane in flight together (loads first, then arithmetic, then stores)
+            constexpr int NM = (NFP + 1) / 2;
+            double qm[NM][4], qp[NM][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { qm[q] = qBase[q * LDQ + own]; qp[q] = fBase[q * LDF + m]; }
+            for (int s2 = 0; s2 < NM; ++s2) {
+                const int m = min(2 * s2 + (lane >> 4), NFP - 1);
+                const int own = fn[m];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { qm[s2][q] = qBase[q * LDQ + own]; qp[s2][q] = fBase[q * LDF + m]; }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < NM; ++s2) {
+                const int m = 2 * s2 + (lane >> 4);
+                double fl[4];
                 if (bc == FACE_INTERIOR) {
-                    const double ps = qm[0] + qp[0];
-                    fl[0] = cm * qm[0] + cp * qp[0] + g0 * (qm[1] + qp[1]) + g1 * (qm[2] + qp[2]) + g2 * (qm[3] + qp[3]);
-                    fl[1] = cm * qm[1] + cp * qp[1] + d0 * ps;
-                    fl[2] = cm * qm[2] + cp * qp[2] + d1 * ps;
-                    fl[3] = cm * qm[3] + cp * qp[3] + d2 * ps;
+                    const double ps = qm[s2][0] + qp[s2][0];
+                    fl[0] = cm * qm[s2][0] + cp * qp[s2][0] + g0 * (qm[s2][1] + qp[s2][1]) + g1 * (qm[s2][2] + qp[s2][2]) + g2 * (qm[s2][3] + qp[s2][3]);
+                    fl[1] = cm * qm[s2][1] + cp * qp[s2][1] + d0 * ps;
+                    fl[2] = cm * qm[s2][2] + cp * qp[s2][2] + d1 * ps;
+                    fl[3] = cm * qm[s2][3] + cp * qp[s2][3] + d2 * ps;
                 } else {
                     const double n[3] = {n0, n1, n2};
-                    faceFlux(bc, 1.0, n, ph, qm, qp, fl);
+                    faceFlux(bc, 1.0, n, ph, qm[s2], qp[s2], fl);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) fl[q] *= fs;
                 }
+                if (m < NFP) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) fBase[q * LDF + m] = fl[q];
+                    for (int q = 0; q < 4; ++q) fBase[q * LDF + m] = fl[q];
+                }
             }
         }
         __syncwarp();
@@ -239,11 +256,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
         PHASE_ADD(1, tp1, tp2);
 
         // ---- 2. B fragments of the volume contraction, then release sQ to the prefetch of the next unit ----
-        double Bq[2][KTQ];
+        double Bq[FLOW ? 2 : 3][KTQ];
+        if constexpr (FLOW) {
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int kt = 0; kt < KTQ; ++kt) Bq[nt][kt] = sQ[(nt * 8 + g) * LDQ + 4 * kt + t];
+                for (int kt = 0; kt < KTQ; ++kt) Bq[nt][kt] = sQ[colQ(nt * 8 + g) + 4 * kt + t];
+        } else {
+            // contravariant velocity in place: columns (vx,vy,vz) of every element become (c_0,c_1,c_2)
+#pragma unroll
+            for (int idx = lane; idx < 4 * NP; idx += 32) {
+                const int el = idx / NP, j = idx - el * NP;
+                const double* Gm = sGeo + el * 9;  // Gm[x*3+u] = du_u/dx_x
+                double* v = sQ + colQ(el * 4 + 1) + j;
+                const double vx = v[0], vy = v[LDQ], vz = v[2 * LDQ];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) v[u * LDQ] = Gm[u] * vx + Gm[3 + u] * vy + Gm[6 + u] * vz;
+            }
+            __syncwarp();
+            // operator u sees the columns (p of elements 0..3 | c_u of elements 0..3)
+            if (g < 4) {
+#pragma unroll
+                for (int kt = 0; kt < KTQ; ++kt) Bq[0][kt] = Bq[1][kt] = Bq[2][kt] = sQ[colQ(g * 4) + 4 * kt + t];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int kt = 0; kt < KTQ; ++kt) Bq[u][kt] = sQ[colQ((g - 4) * 4 + 1 + u) + 4 * kt + t];
+            }
+        }
         __syncwarp();
         prefetch(unit + unitStride, buf ^ 1, flagsNext, nbrNext);
         cpAsyncCommit();
@@ -258,8 +299,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) R[it][nt][0] = R[it][nt][1] = 0.0;
             const double* lRow = sL + g * LDF + t;
-            const double* fRow0 = sFl + g * LDF + t;
-            const double* fRow1 = sFl + (8 + g) * LDF + t;
+            const double* fRow0 = sFl + colF(g) + t;
+            const double* fRow1 = sFl + colF(8 + g) + t;
             double aN[MT], b0N = fRow0[0], b1N = fRow1[0];
 #pragma unroll
             for (int it = 0; it < MT; ++it) aN[it] = lRow[it * 8 * LDF];
@@ -289,8 +330,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
                         const int col = (nt * 2 + elSub) * 4 + fp * 2;
-                        sFl[col * LDF + i] = R[it][nt][0];
-                        sFl[(col + 1) * LDF + i] = R[it][nt][1];
+                        sFl[colF(col) + i] = R[it][nt][0];
+                        sFl[colF(col + 1) + i] = R[it][nt][1];
                     }
                 }
             }
@@ -299,90 +340,154 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
         PHASE_ADD(3, tp3, tp4);
 
         // ---- 4. volume term per m-tile, combined with the per-element constants and added to the staged lift ----
-        // Branch-free combine: the coefficient set of a lane depends on whether its two columns are (p,vx) or (vy,vz).
-        //   own0 += cf0*Ta + cf1*Tb ; own1 += cf0*Tb + cf2*Ta ; send0 += cf3*Ta + cf4*Tb ; send1 += cf5*Ta
-        double cf[2][3][6];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const double* Gm = sGeo + (nt * 2 + elSub) * 9;  // Gm[x*3+u] = du_u/dx_x
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                cf[nt][u][0] = Gm[u] * ph.v0[0] + Gm[3 + u] * ph.v0[1] + Gm[6 + u] * ph.v0[2];
-                cf[nt][u][1] = fp == 0 ? ph.rc2 * Gm[u] : 0.0;
-                cf[nt][u][2] = fp == 0 ? ph.invRho * Gm[u] : 0.0;
-                cf[nt][u][3] = fp == 0 ? ph.invRho * Gm[3 + u] : ph.rc2 * Gm[3 + u];
-                cf[nt][u][4] = fp == 0 ? 0.0 : ph.rc2 * Gm[6 + u];
-                cf[nt][u][5] = fp == 0 ? ph.invRho * Gm[6 + u] : 0.0;
-            }
-        }
-        auto volumeMma = [&](int it, double (&Tacc)[3][2][2]) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) Tacc[u][nt][0] = Tacc[u][nt][1] = 0.0;
-            const double* aRow = sD + (it * 8 + g) * LDQ + t;
-            double aN[3];
-#pragma unroll
-            for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ];
-#pragma unroll
-            for (int kt = 0; kt < KTQ; ++kt) {
-                double a[3];
-#pragma unroll
-                for (int u = 0; u < 3; ++u) a[u] = aN[u];
-                if (kt + 1 < KTQ) {
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ + 4 * (kt + 1)];
-                }
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    dmma884(Tacc[u][0][0], Tacc[u][0][1], a[u], Bq[0][kt]);
-                    dmma884(Tacc[u][1][0], Tacc[u][1][1], a[u], Bq[1][kt]);
-                }
-            }
-        };
-        auto combine = [&](int it, const double (&Tacc)[3][2][2]) {
-            const int i = it * 8 + g;
-#pragma unroll
+        if constexpr (FLOW) {
+            // Branch-free combine: the coefficient set of a lane depends on whether its two columns are (p,vx) or (vy,vz).
+            //   own0 += cf0*Ta + cf1*Tb ; own1 += cf0*Tb + cf2*Ta ; send0 += cf3*Ta + cf4*Tb ; send1 += cf5*Ta
+            double cf[2][3][6];
+    #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                double own0 = 0.0, own1 = 0.0, send0 = 0.0, send1 = 0.0;
-#pragma unroll
+                const double* Gm = sGeo + (nt * 2 + elSub) * 9;  // Gm[x*3+u] = du_u/dx_x
+    #pragma unroll
                 for (int u = 0; u < 3; ++u) {
-                    const double Ta = Tacc[u][nt][0], Tb = Tacc[u][nt][1];
-                    const double* c = cf[nt][u];
-                    own0 = fma(c[0], Ta, own0);
-                    own0 = fma(c[1], Tb, own0);
-                    own1 = fma(c[0], Tb, own1);
-                    own1 = fma(c[2], Ta, own1);
-                    send0 = fma(c[3], Ta, send0);
-                    send0 = fma(c[4], Tb, send0);
-                    send1 = fma(c[5], Ta, send1);
-                }
-                const double recv0 = __shfl_xor_sync(0xffffffffu, send0, 1);
-                const double recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-                // (p,vx) lanes: p += partner's divergence part, vx complete; (vy,vz) lanes: each gets its pressure-gradient part
-                if (i < NP) {
-                    const int col = (nt * 2 + elSub) * 4 + fp * 2;
-                    sFl[col * LDF + i] += own0 + recv0;
-                    sFl[(col + 1) * LDF + i] += fp == 0 ? own1 : own1 + recv1;
+                    cf[nt][u][0] = Gm[u] * ph.v0[0] + Gm[3 + u] * ph.v0[1] + Gm[6 + u] * ph.v0[2];
+                    cf[nt][u][1] = fp == 0 ? ph.rc2 * Gm[u] : 0.0;
+                    cf[nt][u][2] = fp == 0 ? ph.invRho * Gm[u] : 0.0;
+                    cf[nt][u][3] = fp == 0 ? ph.invRho * Gm[3 + u] : ph.rc2 * Gm[3 + u];
+                    cf[nt][u][4] = fp == 0 ? 0.0 : ph.rc2 * Gm[6 + u];
+                    cf[nt][u][5] = fp == 0 ? ph.invRho * Gm[6 + u] : 0.0;
                 }
             }
-        };
-        {
-            double Ta0[3][2][2], Ta1[3][2][2];
-            volumeMma(0, Ta0);
+            auto volumeMma = [&](int it, double (&Tacc)[3][2][2]) {
+    #pragma unroll
+                for (int u = 0; u < 3; ++u)
+    #pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) Tacc[u][nt][0] = Tacc[u][nt][1] = 0.0;
+                const double* aRow = sD + (it * 8 + g) * LDQ + t;
+                double aN[3];
+    #pragma unroll
+                for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ];
+    #pragma unroll
+                for (int kt = 0; kt < KTQ; ++kt) {
+                    double a[3];
+    #pragma unroll
+                    for (int u = 0; u < 3; ++u) a[u] = aN[u];
+                    if (kt + 1 < KTQ) {
+    #pragma unroll
+                        for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ + 4 * (kt + 1)];
+                    }
+    #pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        dmma884(Tacc[u][0][0], Tacc[u][0][1], a[u], Bq[0][kt]);
+                        dmma884(Tacc[u][1][0], Tacc[u][1][1], a[u], Bq[1][kt]);
+                    }
+                }
+            };
+            auto combine = [&](int it, const double (&Tacc)[3][2][2]) {
+                const int i = it * 8 + g;
+    #pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    double own0 = 0.0, own1 = 0.0, send0 = 0.0, send1 = 0.0;
+    #pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const double Ta = Tacc[u][nt][0], Tb = Tacc[u][nt][1];
+                        const double* c = cf[nt][u];
+                        own0 = fma(c[0], Ta, own0);
+                        own0 = fma(c[1], Tb, own0);
+                        own1 = fma(c[0], Tb, own1);
+                        own1 = fma(c[2], Ta, own1);
+                        send0 = fma(c[3], Ta, send0);
+                        send0 = fma(c[4], Tb, send0);
+                        send1 = fma(c[5], Ta, send1);
+                    }
+                    const double recv0 = __shfl_xor_sync(0xffffffffu, send0, 1);
+                    const double recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+                    // (p,vx) lanes: p += partner's divergence part, vx complete; (vy,vz) lanes: each gets its pressure-gradient part
+                    if (i < NP) {
+                        const int col = (nt * 2 + elSub) * 4 + fp * 2;
+                        sFl[colF(col) + i] += own0 + recv0;
+                        sFl[colF(col + 1) + i] += fp == 0 ? own1 : own1 + recv1;
+                    }
+                }
+            };
+            {
+                double Ta0[3][2][2], Ta1[3][2][2];
+                volumeMma(0, Ta0);
+    #pragma unroll 1
+                for (int it = 1; it + 1 < MT; it += 2) {  // two tiles per trip so that the two accumulator sets keep their names
+                    volumeMma(it, Ta1);
+                    combine(it - 1, Ta0);
+                    volumeMma(it + 1, Ta0);
+                    combine(it, Ta1);
+                }
+                if ((MT & 1) == 0) {
+                    volumeMma(MT - 1, Ta1);
+                    combine(MT - 2, Ta0);
+                    combine(MT - 1, Ta1);
+                } else {
+                    combine(MT - 1, Ta0);
+                }
+            }
+        } else {
+            // lanes t < 2 hold T^u_p of elements (2t, 2t+1): they finish the three velocity equations;
+            // lanes t >= 2 hold Dw^u c_u of elements (2(t-2), 2(t-2)+1): they finish the pressure equation.
+            const int eA = (t & 1) * 2;
+            double gw[2][9];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gw[c][k] = ph.invRho * sGeo[(eA + c) * 9 + k];
+            auto volumeMma0 = [&](int it, double (&Tacc)[3][2]) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) Tacc[u][0] = Tacc[u][1] = 0.0;
+                const double* aRow = sD + (it * 8 + g) * LDQ + t;
+                double aN[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ];
+#pragma unroll
+                for (int kt = 0; kt < KTQ; ++kt) {
+                    double a[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) a[u] = aN[u];
+                    if (kt + 1 < KTQ) {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) aN[u] = aRow[u * NPP * LDQ + 4 * (kt + 1)];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) dmma884(Tacc[u][0], Tacc[u][1], a[u], Bq[u][kt]);
+                }
+            };
+            auto combine0 = [&](int it, const double (&Tacc)[3][2]) {
+                const int i = it * 8 + g;
+                if (i < NP) {
+                    if (t < 2) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int x = 0; x < 3; ++x) {
+                                const double r = gw[c][x * 3] * Tacc[0][c] + gw[c][x * 3 + 1] * Tacc[1][c] + gw[c][x * 3 + 2] * Tacc[2][c];
+                                sFl[colF((eA + c) * 4 + 1 + x) + i] += r;
+                            }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) sFl[colF((eA + c) * 4) + i] += ph.rc2 * ((Tacc[0][c] + Tacc[1][c]) + Tacc[2][c]);
+                    }
+                }
+            };
+            double Ta0[3][2], Ta1[3][2];
+            volumeMma0(0, Ta0);
 #pragma unroll 1
-            for (int it = 1; it + 1 < MT; it += 2) {  // two tiles per trip so that the two accumulator sets keep their names
-                volumeMma(it, Ta1);
-                combine(it - 1, Ta0);
-                volumeMma(it + 1, Ta0);
-                combine(it, Ta1);
+            for (int it = 1; it + 1 < MT; it += 2) {
+                volumeMma0(it, Ta1);
+                combine0(it - 1, Ta0);
+                volumeMma0(it + 1, Ta0);
+                combine0(it, Ta1);
             }
             if ((MT & 1) == 0) {
-                volumeMma(MT - 1, Ta1);
-                combine(MT - 2, Ta0);
-                combine(MT - 1, Ta1);
+                volumeMma0(MT - 1, Ta1);
+                combine0(MT - 2, Ta0);
+                combine0(MT - 1, Ta1);
             } else {
-                combine(MT - 1, Ta0);
+                combine0(MT - 1, Ta0);
             }
         }
         __syncwarp();
@@ -414,7 +519,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
                     const int idx = s2 * 32 + lane;
                     if (idx < nValid) {
                         const int el = idx / NP, i = idx - el * NP;
-                        rkApplyK(A, q * S + (int64_t)e0 * NP + idx, sFl[(el * 4 + q) * LDF + i], uv[q][s2], av[q][s2]);
+                        rkApplyK(A, q * S + (int64_t)e0 * NP + idx, sFl[colF(el * 4 + q) + i], uv[q][s2], av[q][s2]);
                     }
                 }
         }
@@ -427,8 +532,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stageTiledKernel(DeviceMesh M,
     cpAsyncWaitAll();
 }
 
-template <int P>
-void launchTiled(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
+template <int P, bool FLOW>
+void launchTiledImpl(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using T = TetTile<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
@@ -439,12 +544,18 @@ void launchTiled(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(stageTiledKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(stageTiledKernel<P, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     const int nUnits = (nEl + 3) / 4;
     const int grid = std::max(1, std::min(numSm, (nUnits + kWarps - 1) / kWarps));
-    stageTiledKernel<P><<<grid, kWarps * 32, smem, s>>>(M, A, nUnits);
+    stageTiledKernel<P, FLOW><<<grid, kWarps * 32, smem, s>>>(M, A, nUnits);
+}
+
+template <int P>
+void launchTiled(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
+    if (M.v0[0] == 0.0 && M.v0[1] == 0.0 && M.v0[2] == 0.0) launchTiledImpl<P, false>(M, A, s);
+    else launchTiledImpl<P, true>(M, A, s);
 }
 
 }  // namespace
