@@ -126,7 +126,8 @@ struct dgb_handle {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
     std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
     int stageEvUsed = 0;
-    StageKernel generic, tiled, active;
+    StageKernel generic, tiled, ws, active;
+    StageKernel autoKernel() const { return ws.launch ? ws : tiled.launch ? tiled : generic; }
     int overlap = 1;
     int timeStages = 1;
     // sources
@@ -420,7 +421,8 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         h->generic = selectGenericKernel(dim, d->order);
         h->tiled = selectTiledKernel(dim, d->order);
         if (!h->generic.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no stage kernel for this dim/order");
-        h->active = h->tiled.launch ? h->tiled : h->generic;
+        if (M.v0[0] == 0.0 && M.v0[1] == 0.0 && M.v0[2] == 0.0) h->ws = selectWsKernel(dim, d->order);
+        h->active = h->autoKernel();
 
         if (h->partitioned) {
             CUDA_CHECK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
@@ -773,7 +775,10 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             else if (value == 2) {
                 if (!h->tiled.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no tiled kernel for this dim/order");
                 h->active = h->tiled;
-            } else h->active = h->tiled.launch ? h->tiled : h->generic;
+            } else if (value == 3) {
+                if (!h->ws.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no warp-specialised kernel for this dim/order/mean flow");
+                h->active = h->ws;
+            } else h->active = h->autoKernel();
         } else if (k == "overlap") h->overlap = value ? 1 : 0;
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;
         else throw DgbException(DGB_ERR_ARG, "unknown option " + k);

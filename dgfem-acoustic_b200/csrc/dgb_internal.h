@@ -63,6 +63,7 @@ struct StageKernel {
 };
 StageKernel selectGenericKernel(int dim, int order);
 StageKernel selectTiledKernel(int dim, int order);  // launch == nullptr if no tiled instance exists
+StageKernel selectWsKernel(int dim, int order);     // warp-specialised DMMA kernel, zero mean flow only (stage_ws.cu)
 
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);

@@ -20,6 +20,7 @@ def main():
     import torch.distributed as dist
 
     out_dir, cells, order, steps, overlap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    flow = int(sys.argv[6]) if len(sys.argv) > 6 else 1  # 0: zero mean flow (warp-specialised kernel at orders 3, 4)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,7 +30,7 @@ def main():
     cfg.add_initial_condition(1.0, -2.0, 0.5, 30.0, 1.0)
     cfg.add_source(2.0, 1.0, 0.0, 6.0, 10.0, 1500.0, 0.0, 1.0)
     mesh = pkg.Mesh(model, cfg)
-    mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * (2 * order + 1)))
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0) if flow else (0.0, 0.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * (2 * order + 1)))
     b = np.nonzero(mesh.fIsBoundary)[0]
     mesh.fBC[b[::3]] = 1
     part = np.zeros(mesh.K, dtype=np.int32)

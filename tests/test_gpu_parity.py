@@ -218,29 +218,63 @@ def test_error_behaviour(pkg, mesh_dir):
         eng.set_option("no_such_option", 1)
 
 
+KERNEL_IDS = {"generic": 1, "tiled": 2, "ws": 3}
+
+
 @pytest.mark.parametrize("name,order,v0", [("cube.msh", 3, (30.0, 10.0, 5.0)), ("sphere.msh", 4, (0, 0, 0)), ("cube:5", 4, (30.0, 10.0, 0.0)),
-                                           ("cube:3", 3, (0.0, 0.0, 0.0))])
-def test_tiled_dmma_kernel_vs_generic_and_oracle(pkg, oracle_mod, mesh_dir, name, order, v0):
-    """The FP64 tensor-core (DMMA) kernel and the CUDA-core kernel are two implementations of the same operator."""
+                                           ("cube:3", 3, (0.0, 0.0, 0.0)), ("cube.msh", 4, (0.0, 0.0, 0.0)), ("cube:1", 4, (0.0, 0.0, 0.0))])
+def test_dmma_kernels_vs_generic_and_oracle(pkg, oracle_mod, mesh_dir, name, order, v0):
+    """The FP64 tensor-core kernels (tiled; warp-specialised for zero mean flow) and the CUDA-core kernel are independent
+    implementations of the same operator. cube:1 (6 elements) and the shipped meshes give ragged last tiles."""
     mesh = build_mesh(pkg, mesh_dir, name, order, v0)
     u = np.random.default_rng(5).standard_normal((4, mesh.N))
     ref = oracle_mod.Oracle(mesh).eval_rhs(oracle_mod.Oracle.OPERATOR, u)
     eng = pkg.Engine(mesh)
-    assert "tiled" in eng.kernel_name
-    tiled = eng.eval_rhs(u)
-    eng.set_option("kernel", 1)
-    assert "generic" in eng.kernel_name
-    generic = eng.eval_rhs(u)
-    for q in range(4):
-        assert rel_l2(tiled[q], ref[q]) < 1e-12
-        assert rel_l2(generic[q], ref[q]) < 1e-12
-    # and through a few RK4 steps with each kernel
+    kernels = ["generic", "tiled"] + (["ws"] if all(v == 0 for v in v0) else [])
+    assert ("ws" if "ws" in kernels else "tiled") in eng.kernel_name  # the automatic choice
+    for kern in kernels:
+        eng.set_option("kernel", KERNEL_IDS[kern])
+        assert kern in eng.kernel_name
+        got = eng.eval_rhs(u)
+        for q in range(4):
+            assert rel_l2(got[q], ref[q]) < 1e-12, (kern, q)
+    # and through a few RK4 / Euler steps with each kernel
     u0 = smooth_state(mesh)
-    out = {}
-    for kern in (1, 2):
-        eng.set_option("kernel", kern)
-        eng.set_state(u0)
-        eng.run(pkg.RUNGE_KUTTA, 0.0, 5)
-        out[kern] = eng.get_state()
+    for integ, steps in ((pkg.RUNGE_KUTTA, 5), (pkg.EULER1, 3)):
+        out = {}
+        for kern in kernels:
+            eng.set_option("kernel", KERNEL_IDS[kern])
+            eng.set_state(u0)
+            eng.run(integ, 0.0, steps)
+            out[kern] = eng.get_state()
+        for kern in kernels[1:]:
+            for q in range(4):
+                assert rel_l2(out[kern][q], out["generic"][q]) < 1e-12, (kern, q)
+
+
+def test_ws_kernel_rk4_vs_oracle_many_tiles(pkg, oracle_mod, mesh_dir):
+    """Warp-specialised kernel over many tiles per CTA (ring buffers wrap several times), against the oracle."""
+    mesh = build_mesh(pkg, mesh_dir, "cube:9", 4, (0.0, 0.0, 0.0))  # 4374 tets = 547 tiles -> 3-4 tiles per CTA
+    u0 = smooth_state(mesh)
+    eng = pkg.Engine(mesh)
+    assert "ws" in eng.kernel_name
+    eng.set_state(u0)
+    eng.run(pkg.RUNGE_KUTTA, 0.0, 10)
+    got = eng.get_state()
+    ref = u0.copy()
+    oracle_mod.Oracle(mesh).run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, ref, 0.0, 10)
     for q in range(4):
-        assert rel_l2(out[2][q], out[1][q]) < 1e-12
+        assert rel_l2(got[q], ref[q]) < TOL
+
+
+def test_ws_kernel_deep_rings(pkg, mesh_dir):
+    """48 000 tets = 6000 tiles (40 per CTA): the warp-specialised kernel against the CUDA-core kernel."""
+    mesh = build_mesh(pkg, mesh_dir, "cube:20", 4, (0.0, 0.0, 0.0))
+    u = np.random.default_rng(11).standard_normal((4, mesh.N))
+    eng = pkg.Engine(mesh)
+    assert "ws" in eng.kernel_name
+    a = eng.eval_rhs(u)
+    eng.set_option("kernel", 1)
+    b = eng.eval_rhs(u)
+    for q in range(4):
+        assert rel_l2(a[q], b[q]) < 1e-12

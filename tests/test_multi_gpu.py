@@ -20,14 +20,14 @@ def _device_count():
         return 0
 
 
-@pytest.mark.parametrize("world,cells,order,overlap", [(2, 6, 4, 1), (2, 6, 4, 0), (2, 5, 2, 1)])
-def test_partitioned_equals_single(tmp_path, world, cells, order, overlap):
+@pytest.mark.parametrize("world,cells,order,overlap,flow", [(2, 6, 4, 1, 1), (2, 6, 4, 0, 1), (2, 5, 2, 1, 1), (2, 6, 4, 1, 0), (2, 7, 4, 0, 0)])
+def test_partitioned_equals_single(tmp_path, world, cells, order, overlap, flow):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     worker = Path(__file__).resolve().parent / "multi_gpu_worker.py"
     steps = 12
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29000 + overlap * 7 + order), str(worker), str(tmp_path), str(cells), str(order), str(steps), str(overlap)]
+           "--master-port", str(29000 + overlap * 7 + order + 20 * flow + cells), str(worker), str(tmp_path), str(cells), str(order), str(steps), str(overlap), str(flow)]
     subprocess.run(cmd, check=True, timeout=600)
     single = np.load(tmp_path / "single.npz")
     merged = np.zeros_like(single["u"])
