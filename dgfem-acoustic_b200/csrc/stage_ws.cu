@@ -32,10 +32,10 @@ namespace dgb {
 namespace {
 
 constexpr int kMaxMapsWs = 64;
-constexpr int kMmaWarps = 4, kSvcWarps = 8, kThreadsWs = (kMmaWarps + kSvcWarps) * 32;
+constexpr int kMmaWarps = 4, kFrontWarps = 8, kBackWarps = 4, kThreadsWs = (kMmaWarps + kFrontWarps + kBackWarps) * 32;
 constexpr int kTileEl = 8;       // elements per tile = rows of one m8n8k4 A fragment
-constexpr int kInStages = 2, kOutStages = 2, kGeoStages = 3;
-constexpr int kRegsMma = 216, kRegsSvc = 144;  // 128*216 + 256*144 = 64512 <= 65536
+constexpr int kInStages = 2, kOutStages = 2, kGeoStages = 8;  // powers of two; geometry must outlive the back warps' lag
+constexpr int kRegsMma = 184, kRegsFront = 112, kRegsBack = 104;  // 128*184 + 256*112 + 128*104 = 65536
 
 __host__ __device__ constexpr int padTo8mod16(int n) {
     int ld = (n + 1) / 2 * 2;
@@ -249,27 +249,15 @@ __device__ __forceinline__ void mmaWarp(const DeviceMesh& M, const StageArgs& A,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// service warps
+// front warps: warp s owns element s of every tile (loads, contravariant velocities, numerical flux)
 // ------------------------------------------------------------------------------------------------------------------
-// k = dt L(y) combined with the RK registers; MODE is a compile-time constant here (see rkApplyK in dgb_device.cuh)
-template <int MODE>
-__device__ __forceinline__ void rkStore(const StageArgs& A, int64_t gi, double k, double uval, double accval) {
-    if constexpr (MODE == MODE_RK1) { A.acc[gi] = k; A.yout[gi] = fma(0.5, k, uval); }
-    else if constexpr (MODE == MODE_RK2) { A.acc[gi] = fma(2.0, k, accval); A.yout[gi] = fma(0.5, k, uval); }
-    else if constexpr (MODE == MODE_RK3) { A.acc[gi] = fma(2.0, k, accval); A.yout[gi] = uval + k; }
-    else if constexpr (MODE == MODE_RK4) { A.u[gi] = fma(accval + k, 1.0 / 6.0, uval); }
-    else if constexpr (MODE == MODE_EULER) { A.yout[gi] = uval + k; }
-    else { A.yout[gi] = k; }
-}
-
 template <int P>
-__device__ __forceinline__ void serviceWarp(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int s, int lane) {
+__device__ __forceinline__ void frontWarp(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int s, int lane) {
     using C = WsCfg<P>;
-    constexpr int NP = C::NP, NFP = C::NFP, NF = C::NF, NFL = C::NFL, KQ = C::KQ, LDI = C::LDI, LDO = C::LDO;
+    constexpr int NP = C::NP, NFP = C::NFP, NF = C::NF, NFL = C::NFL, KQ = C::KQ, LDI = C::LDI;
     constexpr int NA = NP < 32 ? NP : 32, NB = NP - NA;  // nodes handled by lane j (pass A) and by lanes 0..NB-1 as node 32+lane (pass B)
     constexpr int NFB = NFP - 8;                         // face nodes 8.. of a face are handled in the second flux pass
-    constexpr int PS = kTileEl * LDO;                    // output panel stride
-    static_assert(NB >= 0 && 4 * NB <= 32 && NFB > 0 && NFB <= 8, "lane mappings assume 20 <= NP <= 40, 8 < NFP <= 16");
+    static_assert(NB >= 0 && NB <= 32 && NFB > 0 && NFB <= 8, "lane mappings assume NP <= 64, 8 < NFP <= 16");
     const Phys ph = makePhys(M);
     const int64_t S = M.stride;
     // flux lanes: face lf, face node ml (first pass) and 8 + ml (second pass, ml < NFB); all per-lane constants
@@ -277,59 +265,53 @@ __device__ __forceinline__ void serviceWarp(const DeviceMesh& M, const StageArgs
     const bool act1 = ml < NFB;
     const int own0 = sm.faceNodes[lf * NFP + ml], own1 = sm.faceNodes[lf * NFP + (act1 ? 8 + ml : 0)];
     const int slot0 = C::faceSlot(lf, ml), slot1 = C::faceSlot(lf, act1 ? 8 + ml : 8);
-    // epilogue pass B lanes: (field qB, node iB)
-    const int qB = NB > 0 ? min(lane / (NB > 0 ? NB : 1), 3) : 0, iB = NB > 0 ? 32 + lane % (NB > 0 ? NB : 1) : 0;
-    const bool actB = NB > 0 && lane < 4 * NB;
     const bool actA = lane < NA, actQB = lane < NB;
+    // the four fields of the stage input
+    const double* const y0 = A.yin;
+    const double* const y1 = y0 + S;
+    const double* const y2 = y1 + S;
+    const double* const y3 = y2 + S;
 
     unsigned long long* full = sm.bars;
     unsigned long long* inEmpty = sm.bars + kInStages;
-    unsigned long long* outFull = sm.bars + 2 * kInStages;
-    unsigned long long* outEmpty = sm.bars + 2 * kInStages + kOutStages;
     double* const stg = sm.stg + s * C::LDS_;
+    const int eStep = (int)gridDim.x * kTileEl;
+    const int eLast = A.eEnd - 1;
+    int eNext = A.eBegin + (int)blockIdx.x * kTileEl + s;  // element of the tile whose loads are issued next
 
-    auto elemOf = [&](int it) { return A.eBegin + (int)(blockIdx.x + (unsigned)it * gridDim.x) * kTileEl + s; };
-    auto loadMeta = [&](int it, int& flags, int& nbr) {
-        flags = FACE_ABSORBING;
-        nbr = -1;
-        if (it < nIt) {
-            const int e = elemOf(it);
-            if (e < A.eEnd) { flags = M.fflags[e * NF + lf]; nbr = M.fnbr[e * NF + lf]; }
-        }
+    // Face metadata of element e (clamped: rows past the end of the range are computed on a copy of the last element and
+    // never stored)
+    auto loadMeta = [&](int e, int& flags, int& nbr) {
+        const int ec = min(e, eLast);
+        flags = M.fflags[ec * NF + lf];
+        nbr = M.fnbr[ec * NF + lf];
     };
-    // Everything element s of tile `it` needs: nodal values and neighbour traces into registers, geometry into shared memory
-    auto issueLoads = [&](int it, int flags, int nbr, double (&qv)[2][4], double (&tr)[2][4]) {
-        const int e = elemOf(it);
-        const bool valid = e < A.eEnd;
-        const double* src = A.yin + (int64_t)(valid ? e : 0) * NP + lane;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            qv[0][q] = (valid && actA) ? src[q * S] : 0.0;
-            qv[1][q] = (valid && actQB) ? src[q * S + 32] : 0.0;
-        }
-        const bool interior = valid && ((flags & FLAG_BC_MASK) == FACE_INTERIOR) && nbr >= 0;
+    // Everything the element needs: nodal values and neighbour traces into registers, geometry into shared memory.
+    // Boundary faces read their own element instead of a neighbour (the value is ignored by the boundary fluxes).
+    auto issueLoads = [&](int e, int geoSlot, int flags, int nbr, double (&qv)[2][4], double (&tr)[2][4]) {
+        const int ec = min(e, eLast);
+        const unsigned off = (unsigned)ec * NP + lane;
+        if (actA) { qv[0][0] = y0[off]; qv[0][1] = y1[off]; qv[0][2] = y2[off]; qv[0][3] = y3[off]; }
+        if (NB > 0 && actQB) { qv[1][0] = y0[off + 32]; qv[1][1] = y1[off + 32]; qv[1][2] = y2[off + 32]; qv[1][3] = y3[off + 32]; }
+        const bool interior = ((flags & FLAG_BC_MASK) == FACE_INTERIOR) && nbr >= 0;
         const int mapId = flags >> FLAG_MAP_SHIFT;
-        int nn0 = 0, nn1 = 0;
+        int nn0 = own0, nn1 = own1;
         if (interior) {
             const unsigned char* mp = mapId < kMaxMapsWs ? sm.maps + mapId * NFP : M.nbrMaps + mapId * NFP;
             nn0 = mp[ml];
             nn1 = mp[act1 ? 8 + ml : 0];
         }
-        const double* t0 = A.yin + (int64_t)(interior ? nbr : 0) * NP;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            tr[0][q] = interior ? t0[q * S + nn0] : 0.0;
-            tr[1][q] = (interior && act1) ? t0[q * S + nn1] : 0.0;
-        }
-        double* geo = sm.geo + (it % kGeoStages) * C::GEO_TILE + s * C::LDG_;
-        if (lane < 9) cpAsync8z(&geo[lane], M.Ginv + (int64_t)(valid ? e : 0) * 9 + lane, valid);
-        else if (lane >= 16) cpAsync8z(&geo[lane], M.fgeo + (int64_t)(valid ? e : 0) * 16 + (lane - 16), valid);
+        const unsigned tb = (unsigned)(interior ? nbr : ec) * NP;
+        const unsigned t0 = tb + nn0, t1 = tb + nn1;
+        tr[0][0] = y0[t0]; tr[0][1] = y1[t0]; tr[0][2] = y2[t0]; tr[0][3] = y3[t0];
+        tr[1][0] = y0[t1]; tr[1][1] = y1[t1]; tr[1][2] = y2[t1]; tr[1][3] = y3[t1];
+        double* geo = sm.geo + geoSlot * C::GEO_TILE + s * C::LDG_;
+        if (lane < 9) cpAsync8z(&geo[lane], M.Ginv + (size_t)ec * 9 + lane, true);
+        else if (lane >= 16) cpAsync8z(&geo[lane], M.fgeo + (size_t)ec * 16 + (lane - 16), true);
     };
 
-    // contravariant velocities + numerical flux of tile `it` into the input row of element s
-    auto prepAndFlux = [&](int it, int flags, const double (&qv)[2][4], const double (&tr)[2][4]) {
-        double* inRow = sm.in + (it % kInStages) * C::IN_TILE + s * LDI;
-        const double* geo = sm.geo + (it % kGeoStages) * C::GEO_TILE + s * C::LDG_;
+    // contravariant velocities + numerical flux into the input row of element s
+    auto prepAndFlux = [&](double* inRow, const double* geo, int flags, const double (&qv)[2][4], const double (&tr)[2][4]) {
         {
             // p and c_u = rho0 c0^2 sum_x G_xu v_x   (Ginv[x*3+u] = du_u/dx_x); raw velocities staged for the flux gather
             double Gs[9];
@@ -392,102 +374,118 @@ __device__ __forceinline__ void serviceWarp(const DeviceMesh& M, const StageArgs
         }
     };
 
-    const bool needU = A.mode != MODE_RHS;
-    const bool needAcc = A.mode >= MODE_RK2 && A.mode <= MODE_RK4;
-    const double* uSrc = A.mode == MODE_EULER ? A.yin : A.u;
-    // RK registers of element s of tile `it`: [0..3] node `lane` of the four fields, [4] the pass-B entry of this lane
-    auto loadRk = [&](int it, double (&uv)[5], double (&av)[5]) {
-        const int e = elemOf(it);
-        const bool valid = e < A.eEnd;
-        const int64_t base = (int64_t)(valid ? e : 0) * NP;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool ok = valid && actA;
-            uv[q] = (ok && needU) ? uSrc[base + q * S + lane] : 0.0;
-            av[q] = (ok && needAcc) ? A.acc[base + q * S + lane] : 0.0;
-        }
-        const bool okB = valid && actB;
-        uv[4] = (okB && needU) ? uSrc[base + qB * S + iB] : 0.0;
-        av[4] = (okB && needAcc) ? A.acc[base + qB * S + iB] : 0.0;
-    };
-    // K-split partial sums + velocity combine + fused RK update of element s of tile `it`
-    auto epilogueImpl = [&](auto modeTag, int it, const double (&uv)[5], const double (&av)[5]) {
-        constexpr int MODE = decltype(modeTag)::value;
-        const int e = elemOf(it);
-        const bool valid = e < A.eEnd;
-        const double* out = sm.out + (it % kOutStages) * C::OUT_TILE + s * LDO;
-        const double* geo = sm.geo + (it % kGeoStages) * C::GEO_TILE + s * C::LDG_;
-        const int64_t base = (int64_t)(valid ? e : 0) * NP;
-        if (actA) {
-            const double* o = out + lane;
-            double k[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) k[q] = (o[(3 + q) * PS] + o[(7 + q) * PS]) + (o[(11 + q) * PS] + o[(15 + q) * PS]);
-            const double T0 = o[0], T1 = o[PS], T2 = o[2 * PS];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) k[1 + x] += ph.invRho * (geo[x * 3] * T0 + geo[x * 3 + 1] * T1 + geo[x * 3 + 2] * T2);
-            if (valid) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) rkStore<MODE>(A, base + q * S + lane, k[q], uv[q], av[q]);
-            }
-        }
-        if (NB > 0 && actB) {
-            const double* o = out + iB;
-            double k = (o[(3 + qB) * PS] + o[(7 + qB) * PS]) + (o[(11 + qB) * PS] + o[(15 + qB) * PS]);
-            if (qB > 0) {
-                const double* Gx = geo + (qB - 1) * 3;
-                k += ph.invRho * (Gx[0] * o[0] + Gx[1] * o[PS] + Gx[2] * o[2 * PS]);
-            }
-            if (valid) rkStore<MODE>(A, base + qB * S + iB, k, uv[4], av[4]);
-        }
-    };
-    auto epilogue = [&](int it, const double (&uv)[5], const double (&av)[5]) {
-        switch (A.mode) {
-            case MODE_RK1: epilogueImpl(std::integral_constant<int, MODE_RK1>{}, it, uv, av); break;
-            case MODE_RK2: epilogueImpl(std::integral_constant<int, MODE_RK2>{}, it, uv, av); break;
-            case MODE_RK3: epilogueImpl(std::integral_constant<int, MODE_RK3>{}, it, uv, av); break;
-            case MODE_RK4: epilogueImpl(std::integral_constant<int, MODE_RK4>{}, it, uv, av); break;
-            case MODE_EULER: epilogueImpl(std::integral_constant<int, MODE_EULER>{}, it, uv, av); break;
-            default: epilogueImpl(std::integral_constant<int, MODE_RHS>{}, it, uv, av); break;
-        }
-    };
-
     int flagsCur, nbrCur, flagsNext, nbrNext;
-    double qv[2][4], tr[2][4], uv[5], av[5];
-    loadMeta(0, flagsCur, nbrCur);
-    issueLoads(0, flagsCur, nbrCur, qv, tr);
+    double qv[2][4], tr[2][4];
+    loadMeta(eNext, flagsCur, nbrCur);
+    issueLoads(eNext, 0, flagsCur, nbrCur, qv, tr);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    loadMeta(1, flagsNext, nbrNext);
+    eNext += eStep;
+    loadMeta(eNext, flagsNext, nbrNext);
 
     for (int it = 0; it < nIt; ++it) {
-        const int b = it % kInStages;
-        // 1. tile it: its input slot is free once the MMA warps are done with tile it - kInStages
+        const int b = it & (kInStages - 1);
+        // tile it: its input slot is free once the MMA warps are done with tile it - kInStages
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         mbarWait(&inEmpty[b], ((it / kInStages) & 1) ^ 1);
-        prepAndFlux(it, flagsCur, qv, tr);
+        prepAndFlux(sm.in + b * C::IN_TILE + s * LDI, sm.geo + (it & (kGeoStages - 1)) * C::GEO_TILE + s * C::LDG_, flagsCur, qv, tr);
         __syncwarp();
         if (lane == 0) mbarArrive(&full[b]);
-        // 2. loads of tile it+1 (registers are free again), face metadata of tile it+2
+        // loads of tile it+1 (the registers are free again), face metadata of tile it+2
         flagsCur = flagsNext; nbrCur = nbrNext;
-        if (it + 1 < nIt) issueLoads(it + 1, flagsCur, nbrCur, qv, tr);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        loadMeta(it + 2, flagsNext, nbrNext);
-        // 3. tile it-1 leaves: partial sums -> RK update
-        if (it >= 1) {
-            const int ob = (it - 1) % kOutStages;
-            mbarWait(&outFull[ob], ((it - 1) / kOutStages) & 1);
-            epilogue(it - 1, uv, av);
-            __syncwarp();
-            if (lane == 0) mbarArrive(&outEmpty[ob]);
+        if (it + 1 < nIt) {
+            issueLoads(eNext, (it + 1) & (kGeoStages - 1), flagsCur, nbrCur, qv, tr);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            eNext += eStep;
+            loadMeta(eNext, flagsNext, nbrNext);
         }
-        loadRk(it, uv, av);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (nIt >= 1) {
-        const int ob = (nIt - 1) % kOutStages;
-        mbarWait(&outFull[ob], ((nIt - 1) / kOutStages) & 1);
-        epilogue(nIt - 1, uv, av);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// back warps: warp q owns field q of every tile (K-split partial sums, velocity combine, fused RK update)
+// ------------------------------------------------------------------------------------------------------------------
+// k = dt L(y) combined with the RK registers; MODE is a compile-time constant here (see rkApplyK in dgb_device.cuh)
+template <int MODE>
+__device__ __forceinline__ void rkStore(double* __restrict__ u, double* __restrict__ acc, double* __restrict__ yout, double k, double uval,
+                                        double accval) {
+    if constexpr (MODE == MODE_RK1) { *acc = k; *yout = fma(0.5, k, uval); }
+    else if constexpr (MODE == MODE_RK2) { *acc = fma(2.0, k, accval); *yout = fma(0.5, k, uval); }
+    else if constexpr (MODE == MODE_RK3) { *acc = fma(2.0, k, accval); *yout = uval + k; }
+    else if constexpr (MODE == MODE_RK4) { *u = fma(accval + k, 1.0 / 6.0, uval); }
+    else if constexpr (MODE == MODE_EULER) { *yout = uval + k; }
+    else { *yout = k; }
+}
+
+template <int P, int MODE>
+__device__ __forceinline__ void backWarpImpl(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int q, int lane) {
+    using C = WsCfg<P>;
+    constexpr int NP = C::NP, LDO = C::LDO;
+    constexpr int PS = kTileEl * LDO;                      // output panel stride
+    constexpr int NV = (kTileEl * NP + 31) / 32;           // passes over the 8*NP values of one field of a tile
+    constexpr bool needU = MODE != MODE_RHS, needAcc = MODE >= MODE_RK2 && MODE <= MODE_RK4;
+    const Phys ph = makePhys(M);
+    const int64_t S = M.stride;
+    unsigned long long* outFull = sm.bars + 2 * kInStages;
+    unsigned long long* outEmpty = sm.bars + 2 * kInStages + kOutStages;
+    // per-pass lane constants: value idx = v*32 + lane of the tile <-> (element el, node i)
+    int oOff[NV], gOff[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int idx = min(v * 32 + lane, kTileEl * NP - 1);
+        const int el = idx / NP, i = idx - el * NP;
+        oOff[v] = el * LDO + i;
+        gOff[v] = el * C::LDG_ + (q > 0 ? (q - 1) * 3 : 0);
+    }
+    const double* uSrc = (MODE == MODE_EULER ? A.yin : A.u) + q * S;
+    double* const uDst = A.u + q * S;
+    double* const accP = A.acc + q * S;
+    double* const youtP = A.yout + q * S;
+    const int eStep = (int)gridDim.x * kTileEl;
+    int e0 = A.eBegin + (int)blockIdx.x * kTileEl;
+
+    for (int it = 0; it < nIt; ++it, e0 += eStep) {
+        const int nVal = min(kTileEl, A.eEnd - e0) * NP;  // valid values of this tile
+        const size_t base = (size_t)e0 * NP + lane;
+        double uv[NV], av[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const bool ok = v * 32 + lane < nVal;
+            uv[v] = (needU && ok) ? uSrc[base + v * 32] : 0.0;
+            av[v] = (needAcc && ok) ? accP[base + v * 32] : 0.0;
+        }
+        const int ob = it & (kOutStages - 1);
+        mbarWait(&outFull[ob], (it / kOutStages) & 1);
+        const double* out = sm.out + ob * C::OUT_TILE;
+        const double* geo = sm.geo + (it & (kGeoStages - 1)) * C::GEO_TILE;
+        double k[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double* o = out + oOff[v];
+            k[v] = (o[(3 + q) * PS] + o[(7 + q) * PS]) + (o[(11 + q) * PS] + o[(15 + q) * PS]);
+            if (q > 0) {
+                const double* Gx = geo + gOff[v];
+                k[v] += ph.invRho * (Gx[0] * o[0] + Gx[1] * o[PS] + Gx[2] * o[2 * PS]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbarArrive(&outEmpty[ob]);
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (v * 32 + lane < nVal) rkStore<MODE>(uDst + base + v * 32, accP + base + v * 32, youtP + base + v * 32, k[v], uv[v], av[v]);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void backWarp(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int q, int lane) {
+    switch (A.mode) {
+        case MODE_RK1: backWarpImpl<P, MODE_RK1>(M, A, sm, nIt, q, lane); break;
+        case MODE_RK2: backWarpImpl<P, MODE_RK2>(M, A, sm, nIt, q, lane); break;
+        case MODE_RK3: backWarpImpl<P, MODE_RK3>(M, A, sm, nIt, q, lane); break;
+        case MODE_RK4: backWarpImpl<P, MODE_RK4>(M, A, sm, nIt, q, lane); break;
+        case MODE_EULER: backWarpImpl<P, MODE_EULER>(M, A, sm, nIt, q, lane); break;
+        default: backWarpImpl<P, MODE_RHS>(M, A, sm, nIt, q, lane); break;
     }
 }
 
@@ -506,14 +504,14 @@ __global__ void __launch_bounds__(kThreadsWs, 1) stageWsKernel(DeviceMesh M, Sta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < kInStages; ++i) { mbarInit(&sm.bars[i], kSvcWarps); mbarInit(&sm.bars[kInStages + i], kMmaWarps); }
-        for (int i = 0; i < kOutStages; ++i) { mbarInit(&sm.bars[2 * kInStages + i], kMmaWarps); mbarInit(&sm.bars[2 * kInStages + kOutStages + i], kSvcWarps); }
+        for (int i = 0; i < kInStages; ++i) { mbarInit(&sm.bars[i], kFrontWarps); mbarInit(&sm.bars[kInStages + i], kMmaWarps); }
+        for (int i = 0; i < kOutStages; ++i) { mbarInit(&sm.bars[2 * kInStages + i], kMmaWarps); mbarInit(&sm.bars[2 * kInStages + kOutStages + i], kBackWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < C::NFL; i += kThreadsWs) sm.faceNodes[i] = M.faceNodes[i];
     const int nMapsS = min(M.nMaps, kMaxMapsWs);
     for (int i = tid; i < nMapsS * C::NFP; i += kThreadsWs) sm.maps[i] = M.nbrMaps[i];
-    // the K padding of the input rows and of the staging area must hold finite values (zeros) for ever
+    // the K padding of the input rows must hold finite values (zeros) for ever
     for (int i = tid; i < kInStages * C::IN_TILE + C::STG_TILE; i += kThreadsWs) sm.in[i] = 0.0;
     __syncthreads();
 
@@ -524,9 +522,12 @@ __global__ void __launch_bounds__(kThreadsWs, 1) stageWsKernel(DeviceMesh M, Sta
         else if (warp == 1) mmaWarp<P, 1>(M, A, sm, nIt, lane);
         else if (warp == 2) mmaWarp<P, 2>(M, A, sm, nIt, lane);
         else mmaWarp<P, 3>(M, A, sm, nIt, lane);
+    } else if (warp < kMmaWarps + kFrontWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsFront));
+        frontWarp<P>(M, A, sm, nIt, warp - kMmaWarps, lane);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsSvc));
-        serviceWarp<P>(M, A, sm, nIt, warp - kMmaWarps, lane);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsBack));
+        backWarp<P>(M, A, sm, nIt, warp - kMmaWarps - kFrontWarps, lane);
     }
 }
 
