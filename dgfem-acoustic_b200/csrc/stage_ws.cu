@@ -48,12 +48,8 @@ struct WsCfg {
     static constexpr int NP = (P + 1) * (P + 2) * (P + 3) / 6, NFP = (P + 1) * (P + 2) / 2, NF = 4, NFL = NF * NFP;
     static constexpr int NT = (NP + 7) / 8, NPP = NT * 8;    // node tiles (n of the MMA)
     static constexpr int KTQ = (NP + 3) / 4, KQ = KTQ * 4;   // k-tiles of a volume block, padded block length
-    // first lift k-tile of every MMA role (role r owns [SLICE[r], SLICE[r+1]))
-    __host__ __device__ static constexpr int slice(int r) {
-        if (P == 4) { constexpr int s[5] = {0, 3, 6, 8, 15}; return s[r]; }
-        constexpr int s[5] = {0, 2, 4, 6, 10};
-        return s[r];
-    }
+    // lift k-tiles owned by each of the MMA roles 0..2 (role r: [r*NSD, (r+1)*NSD)); role 3 owns the rest
+    static constexpr int NSD = P == 4 ? 3 : 2;
     // input row of one element (doubles): p | c_0 | c_1 | c_2 | F_p | F_vx | F_vy | F_vz
     static constexpr int OFF_P = 0, OFF_C = KQ, OFF_F = 4 * KQ;
     static constexpr int LDI = padTo8mod16(4 * KQ + 4 * NFL);
@@ -75,7 +71,7 @@ struct WsCfg {
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ uint32_t sAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cpAsync8z(void* dst, const void* src, bool valid) {
@@ -127,123 +123,151 @@ struct WsSmem {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// MMA warps
+// MMA warps. Roles 0..2 run the SAME instruction stream (only register contents and a few offsets differ) and the
+// repeated jobs are real loops: the per-SM instruction working set has to stay inside the 32 KB L1.5 instruction cache,
+// the loop of one MMA warp inside the ~6 KB L0 of its sub-partition (a DMMA costs 32 B of code with its pacing NOP).
 // ------------------------------------------------------------------------------------------------------------------
-template <int P, int ROLE>
-__device__ __forceinline__ void mmaWarp(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int lane) {
+struct MmaBars {
+    unsigned long long *full, *inEmpty, *outFull, *outEmpty;
+};
+__device__ __forceinline__ MmaBars mmaBars(const WsSmem& sm) {
+    return {sm.bars, sm.bars + kInStages, sm.bars + 2 * kInStages, sm.bars + 2 * kInStages + kOutStages};
+}
+
+// roles 0..2: T^r = Dw^r p ; P_r = Dw^r (rho c^2 c_r) + (-LIFT slice r) F_p ; V_r,x = (-LIFT slice r) F_vx
+template <int P>
+__device__ __forceinline__ void mmaWarpD(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int role, int lane) {
     using C = WsCfg<P>;
-    constexpr int NP = C::NP, NT = C::NT, KTQ = C::KTQ, LDI = C::LDI, LDO = C::LDO, NFL = C::NFL;
-    constexpr int KT0 = C::slice(ROLE), NS = C::slice(ROLE + 1) - C::slice(ROLE);
-    constexpr bool HAS_D = ROLE < 3;
+    constexpr int NP = C::NP, NT = C::NT, KTQ = C::KTQ, LDI = C::LDI, LDO = C::LDO, NFL = C::NFL, NS = C::NSD;
+    constexpr int PS = kTileEl * LDO;
     const int g = lane >> 2, t = lane & 3;
     const double scale = A.mode == MODE_RHS ? 1.0 : A.dt;  // k = dt L(y) leaves the tensor pipe directly
+    const int kt0 = role * NS;
 
     // register-resident operator slice, as B fragments: lane (g, t) holds Op[node 8*nt + g][k(kt, t)]
-    double D[HAS_D ? NT : 1][HAS_D ? KTQ : 1];
+    double D[NT][KTQ], L[NT][NS];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int i = nt * 8 + g;
+#pragma unroll
+        for (int kt = 0; kt < KTQ; ++kt) {
+            const int k = kOfTile(kt, KTQ, t);
+            D[nt][kt] = (i < NP && k < NP) ? scale * M.DwT[((size_t)role * NP + k) * NP + i] : 0.0;
+        }
+#pragma unroll
+        for (int kt = 0; kt < NS; ++kt) {
+            const int k = 4 * kt0 + kOfTile(kt, NS, t);
+            L[nt][kt] = i < NP ? scale * M.nLiftT[(size_t)C::slotFaceNode(k) * NP + i] : 0.0;
+        }
+    }
+    const MmaBars bar = mmaBars(sm);
+    const int rowOff = g * LDI, offC = C::OFF_C + role * C::KQ, offF = C::OFF_F + 4 * kt0;
+    const int outOff = g * LDO + 2 * t, panelT = role * PS, panelP = (3 + role * 4) * PS;
+
+    for (int it = 0; it < nIt; ++it) {
+        const int b = it & (kInStages - 1), ob = it & (kOutStages - 1);
+        const double* row = sm.in + b * C::IN_TILE + rowOff;
+        double* out = sm.out + ob * C::OUT_TILE + outOff;
+        mbarWait(&bar.full[b], (it / kInStages) & 1);
+        mbarWait(&bar.outEmpty[ob], ((it / kOutStages) & 1) ^ 1);
+
+        auto store = [&](double* dst, const double (&acc)[NT][2]) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<double2*>(dst + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
+        };
+        double aP[KTQ], aC[KTQ], aV[NS];
+        loadFrags<KTQ>(aP, row + C::OFF_P, t);
+        loadFrags<KTQ>(aC, row + offC, t);
+        {
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < KTQ; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aP[kt], D[nt][kt]);
+            loadFrags<NS>(aV, row + offF, t);
+            store(out + panelT, acc);
+        }
+        {
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < KTQ; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aC[kt], D[nt][kt]);
+#pragma unroll
+            for (int kt = 0; kt < NS; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aV[kt], L[nt][kt]);
+            loadFrags<NS>(aV, row + offF + NFL, t);
+            store(out + panelP, acc);
+        }
+#pragma unroll 1
+        for (int x = 1; x < 4; ++x) {
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < NS; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aV[kt], L[nt][kt]);
+            loadFrags<NS>(aV, row + offF + (x < 3 ? x + 1 : 3) * NFL, t);  // next field (the last request is a dummy)
+            store(out + panelP + x * PS, acc);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbarArrive(&bar.inEmpty[b]);
+            mbarArrive(&bar.outFull[ob]);
+        }
+    }
+}
+
+// role 3: P_3 and V_3,x with the last slice of -LIFT
+template <int P>
+__device__ __forceinline__ void mmaWarpL(const DeviceMesh& M, const StageArgs& A, const WsSmem& sm, int nIt, int lane) {
+    using C = WsCfg<P>;
+    constexpr int NP = C::NP, NT = C::NT, LDI = C::LDI, LDO = C::LDO, NFL = C::NFL, KT0 = 3 * C::NSD, NS = NFL / 4 - KT0;
+    constexpr int PS = kTileEl * LDO;
+    const int g = lane >> 2, t = lane & 3;
+    const double scale = A.mode == MODE_RHS ? 1.0 : A.dt;
     double L[NT][NS];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int i = nt * 8 + g;
-        if constexpr (HAS_D) {
-#pragma unroll
-            for (int kt = 0; kt < KTQ; ++kt) {
-                const int k = kOfTile(kt, KTQ, t);
-                D[nt][kt] = (i < NP && k < NP) ? scale * M.DwT[((size_t)ROLE * NP + k) * NP + i] : 0.0;
-            }
-        }
 #pragma unroll
         for (int kt = 0; kt < NS; ++kt) {
             const int k = 4 * KT0 + kOfTile(kt, NS, t);
             L[nt][kt] = i < NP ? scale * M.nLiftT[(size_t)C::slotFaceNode(k) * NP + i] : 0.0;
         }
     }
-
-    unsigned long long* full = sm.bars;
-    unsigned long long* inEmpty = sm.bars + kInStages;
-    unsigned long long* outFull = sm.bars + 2 * kInStages;
-    unsigned long long* outEmpty = sm.bars + 2 * kInStages + kOutStages;
-
+    const MmaBars bar = mmaBars(sm);
     for (int it = 0; it < nIt; ++it) {
-        const int b3 = it % kInStages, b2 = it % kOutStages;
-        const double* row = sm.in + b3 * C::IN_TILE + g * LDI;
-        double* out = sm.out + b2 * C::OUT_TILE + g * LDO + 2 * t;  // + panel * 8 * LDO + nt * 8
-        mbarWait(&full[b3], (it / kInStages) & 1);
-        mbarWait(&outEmpty[b2], ((it / kOutStages) & 1) ^ 1);
-
-        auto store = [&](int panel, const double (&acc)[NT][2]) {
+        const int b = it & (kInStages - 1), ob = it & (kOutStages - 1);
+        const double* row = sm.in + b * C::IN_TILE + g * LDI + C::OFF_F + 4 * KT0;
+        double* out = sm.out + ob * C::OUT_TILE + g * LDO + 2 * t + 15 * PS;
+        mbarWait(&bar.full[b], (it / kInStages) & 1);
+        mbarWait(&bar.outEmpty[ob], ((it / kOutStages) & 1) ^ 1);
+        double aV[NS];
+        loadFrags<NS>(aV, row, t);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            double acc[NT][2];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-                *reinterpret_cast<double2*>(out + panel * (kTileEl * LDO) + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
-        };
-
-        if constexpr (HAS_D) {
-            // T^r = Dw^r p, then P_r = Dw^r (rho c^2 c_r) + (-LIFT slice) F_p; the fragments of the next job are requested
-            // before the DMMAs of the current one
-            double aP[KTQ], aC[KTQ], aF[NS];
-            loadFrags<KTQ>(aP, row + C::OFF_P, t);
-            loadFrags<KTQ>(aC, row + C::OFF_C + ROLE * C::KQ, t);
-            double accT[NT][2], accP[NT][2];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) accT[nt][0] = accT[nt][1] = accP[nt][0] = accP[nt][1] = 0.0;
-#pragma unroll
-            for (int kt = 0; kt < KTQ; ++kt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma(accT[nt], aP[kt], D[nt][kt]);
-            loadFrags<NS>(aF, row + C::OFF_F + 4 * KT0, t);
-#pragma unroll
-            for (int kt = 0; kt < KTQ; ++kt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma(accP[nt], aC[kt], D[nt][kt]);
-            store(ROLE, accT);
-            double aV[NS];
-            loadFrags<NS>(aV, row + C::OFF_F + NFL + 4 * KT0, t);
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
             for (int kt = 0; kt < NS; ++kt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma(accP[nt], aF[kt], L[nt][kt]);
-            store(3 + ROLE * 4, accP);
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aV[kt], L[nt][kt]);
+            loadFrags<NS>(aV, row + (q < 3 ? q + 1 : 3) * NFL, t);
 #pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double accV[NT][2];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) accV[nt][0] = accV[nt][1] = 0.0;
-                double aN[NS];
-                if (x < 2) loadFrags<NS>(aN, row + C::OFF_F + (x + 2) * NFL + 4 * KT0, t);
-#pragma unroll
-                for (int kt = 0; kt < NS; ++kt)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(accV[nt], aV[kt], L[nt][kt]);
-                store(3 + ROLE * 4 + 1 + x, accV);
-                if (x < 2) {
-#pragma unroll
-                    for (int kt = 0; kt < NS; ++kt) aV[kt] = aN[kt];
-                }
-            }
-        } else {
-            double aV[NS];
-            loadFrags<NS>(aV, row + C::OFF_F + 4 * KT0, t);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double acc[NT][2];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-                double aN[NS];
-                if (q < 3) loadFrags<NS>(aN, row + C::OFF_F + (q + 1) * NFL + 4 * KT0, t);
-#pragma unroll
-                for (int kt = 0; kt < NS; ++kt)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(acc[nt], aV[kt], L[nt][kt]);
-                store(3 + ROLE * 4 + q, acc);
-                if (q < 3) {
-#pragma unroll
-                    for (int kt = 0; kt < NS; ++kt) aV[kt] = aN[kt];
-                }
-            }
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<double2*>(out + q * PS + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
         }
         __syncwarp();
         if (lane == 0) {
-            mbarArrive(&inEmpty[b3]);
-            mbarArrive(&outFull[b2]);
+            mbarArrive(&bar.inEmpty[b]);
+            mbarArrive(&bar.outFull[ob]);
         }
     }
 }
@@ -518,10 +542,8 @@ __global__ void __launch_bounds__(kThreadsWs, 1) stageWsKernel(DeviceMesh M, Sta
     const int nIt = ((int)blockIdx.x < nTiles) ? (nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp < kMmaWarps) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsMma));
-        if (warp == 0) mmaWarp<P, 0>(M, A, sm, nIt, lane);
-        else if (warp == 1) mmaWarp<P, 1>(M, A, sm, nIt, lane);
-        else if (warp == 2) mmaWarp<P, 2>(M, A, sm, nIt, lane);
-        else mmaWarp<P, 3>(M, A, sm, nIt, lane);
+        if (warp < 3) mmaWarpD<P>(M, A, sm, nIt, warp, lane);
+        else mmaWarpL<P>(M, A, sm, nIt, lane);
     } else if (warp < kMmaWarps + kFrontWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsFront));
         frontWarp<P>(M, A, sm, nIt, warp - kMmaWarps, lane);
