@@ -283,7 +283,7 @@ def load_dgb():
     global _dgb
     if _dgb is not None:
         return _dgb
-    path = LIB_DIR / "libdgb.so"
+    path = Path(os.environ["DGB_LIB"]) if os.environ.get("DGB_LIB") else LIB_DIR / "libdgb.so"  # DGB_LIB: development builds (profiles/build_variant.sh)
     if not path.exists():
         raise DgbError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first "
                        "(the CUDA engine has no CPU fallback)")
