@@ -45,7 +45,14 @@ constexpr int kTileEl = 8;  // elements per tile = rows of one m8n8k4 A fragment
 // inverse-Jacobian ring (a power of two) must outlive the back warps' lag behind the front warps (<= 8 tiles); the
 // face-geometry and nodal-value rings only serve the front warps (prefetch distance 2). The total is kept below 195 KB so
 // that the SM is configured with the 196 KB carve-out and ~60 KB of L1 remain for the neighbour-trace gathers.
-constexpr int kInStages = 3, kOutStages = 3, kGeoStages = 8, kFgStages = 4, kStgStages = 3;
+#ifndef DGB_WS_OUTSTAGES
+#define DGB_WS_OUTSTAGES 3
+#endif
+#ifndef DGB_WS_STGSTAGES
+#define DGB_WS_STGSTAGES 3
+#endif
+constexpr int kInStages = 3, kOutStages = DGB_WS_OUTSTAGES, kGeoStages = 8, kFgStages = 4, kStgStages = DGB_WS_STGSTAGES;
+constexpr int kOwnAhead = kStgStages - 1;  // prefetch distance (tiles) of the nodal values / geometry
 // setmaxnreg only moves registers inside the CTA's launch allocation: 512 threads x 128 registers = 65536
 constexpr int kRegsLaunch = 128, kRegsMma = 184, kRegsFront = 104, kRegsBack = 120;
 static_assert(128 * kRegsMma + 256 * kRegsFront + 128 * kRegsBack <= kThreadsWs * kRegsLaunch, "register budget of the CTA");
@@ -84,20 +91,8 @@ struct WsCfg {
     static_assert(NFL % 4 == 0, "lift contraction length must be a multiple of 4");
 };
 
-#ifndef DGB_WS_GAP
-#define DGB_WS_GAP 0
-#endif
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-#if DGB_WS_GAP > 0
-    // experiment: leave the FP64 pipe idle for a few cycles after every DMMA so that the DFMA/DADD of the service warps
-    // (same pipe) do not queue behind a back-to-back DMMA stream
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-    unsigned dummy = 0;
-#pragma unroll
-    for (int i = 0; i < DGB_WS_GAP; ++i) asm volatile("add.u32 %0, %0, 1;" : "+r"(dummy));
-#else
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-#endif
 }
 __device__ __forceinline__ uint32_t sAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cpAsync8(void* dst, const void* src) {
@@ -119,10 +114,11 @@ __device__ __forceinline__ void mbarWait(unsigned long long* bar, uint32_t parit
     }
 }
 
-// Global accesses of the service warps. The L1 and the shared memory are one data array with one 128 B/clk port, and this
-// kernel keeps that port busy with its shared-memory traffic: streaming data (RK registers, results) and the 8-byte
-// trace gathers should not be filled into L1 lines on their way through (DGB_WS_LDHINT: 0 default caching, 1 streaming
-// hints for the RK registers / results, 2 also no L1 allocation for the gathered traces).
+// Global accesses of the service warps. The L1 and the shared memory are one data array, and what is left of it as L1
+// (~60 KB with the 196 KB carve-out this kernel fits under) is what serves the 8-byte neighbour-trace gathers: measured on
+// B200, a build with 230 KB of shared memory (28 KB of L1) is 19 % slower, and gathers that bypass L1 (DGB_WS_LDHINT=2) are
+// 22 % slower (profiles/r01_ws_ablation.txt). Streaming data (RK registers, results) is therefore marked evict-first
+// (DGB_WS_LDHINT >= 1), the gathers keep the default caching.
 #ifndef DGB_WS_LDHINT
 #define DGB_WS_LDHINT 1
 #endif
@@ -511,45 +507,50 @@ __device__ __forceinline__ void frontWarp(const DeviceMesh& M, const StageArgs& 
         }
     };
 
-    // prefetch distance 2: own values / geometry in the cp.async rings, traces in two register sets
-    int flagsCur, nbrCur, flagsN1, nbrN1, flagsN2, nbrN2;
-    double trCur[2][4], trNext[2][4];
-    loadMeta(eFirst, flagsCur, nbrCur);
-    loadMeta(eFirst + eStep, flagsN1, nbrN1);
-    issueOwn(eFirst, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    issueOwn(eFirst + eStep, 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    loadTraces(eFirst, flagsCur, nbrCur, trCur);
-    loadTraces(eFirst + eStep, flagsN1, nbrN1, trNext);
-    loadMeta(eFirst + 2 * eStep, flagsN2, nbrN2);
-    int e2 = eFirst + 2 * eStep;  // element of tile it + 2
-
+    // Prefetch: own values / geometry kOwnAhead tiles ahead in the cp.async rings, traces two tiles ahead in two register
+    // sets. The loop is unrolled by two so that each set keeps its registers (even / odd tiles): a rotating copy would make
+    // the compiler wait for the loads it has just issued.
+    int eIt = eFirst;  // element of the tile in hand
     Ring<kInStages> in;
-    for (int it = 0; it < nIt; ++it, e2 += eStep, in.next()) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // own values / geometry of tile it have landed
+    int it = 0;
+    auto step = [&](int& flagsX, int& nbrX, double (&trX)[2][4], int& flagsP, int& nbrP) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kOwnAhead - 1) : "memory");  // own values / geometry of tile it have landed
         __syncwarp();
         mbarWait(&bar.inEmpty[in.b], in.phase ^ 1);            // the MMA warps are done with tile it - kInStages
 #ifndef DGB_WS_NOFRONT
         prepAndFlux(sm.in + in.b * C::IN_TILE + s * LDI, sm.stg + (it % kStgStages) * C::STG_TILE + s * C::LDS_,
                     sm.geo + (it & (kGeoStages - 1)) * C::GEO_TILE + s * C::LDG_, sm.fg + (it & (kFgStages - 1)) * C::FG_TILE + s * C::LDFG,
-                    flagsCur, trCur);
+                    flagsX, trX);
 #endif
         __syncwarp();
         if (lane == 0) mbarArrive(&bar.full[in.b]);
-        // rotate, then refill the pipeline with tile it + 2 (face metadata of tile it + 3)
-#pragma unroll
-        for (int v = 0; v < 2; ++v)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) trCur[v][q] = trNext[v][q];
-        flagsCur = flagsN1; nbrCur = nbrN1;
-        flagsN1 = flagsN2; nbrN1 = nbrN2;
-        issueOwn(e2, it + 2);
+        // refill: own values of tile it + kOwnAhead, traces of tile it + 2 (same register set), face metadata of tile it + 3
+        issueOwn(eIt + kOwnAhead * eStep, it + kOwnAhead);
         asm volatile("cp.async.commit_group;" ::: "memory");
+        flagsX = flagsP; nbrX = nbrP;
 #ifndef DGB_WS_NOTRACES
-        loadTraces(e2, flagsN1, nbrN1, trNext);
+        loadTraces(eIt + 2 * eStep, flagsX, nbrX, trX);
 #endif
-        loadMeta(e2 + eStep, flagsN2, nbrN2);
+        loadMeta(eIt + 3 * eStep, flagsP, nbrP);
+        eIt += eStep;
+        in.next();
+        ++it;
+    };
+    int flagsA, nbrA, flagsB, nbrB, flagsP, nbrP;
+    double trA[2][4], trB[2][4];
+    loadMeta(eFirst, flagsA, nbrA);
+    loadMeta(eFirst + eStep, flagsB, nbrB);
+#pragma unroll
+    for (int d = 0; d < kOwnAhead; ++d) {
+        issueOwn(eFirst + d * eStep, d);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    loadTraces(eFirst, flagsA, nbrA, trA);
+    loadTraces(eFirst + eStep, flagsB, nbrB, trB);
+    loadMeta(eFirst + 2 * eStep, flagsP, nbrP);
+    while (it < nIt) {
+        step(flagsA, nbrA, trA, flagsP, nbrP);
+        if (it < nIt) step(flagsB, nbrB, trB, flagsP, nbrP);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
