@@ -53,51 +53,81 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs: NVML polled every few milliseconds from a
+    thread (nvidia-ml-py), `nvidia-smi -lms` as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                   "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                   "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                   "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, self.max_mhz, [k for k, bit in reasons.items() if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((float(r[0]), float(r[1]), [nm for k, nm in enumerate(names) if r[3 + k].lower().startswith("active")]))
+            except Exception:
+                continue
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(r[1] for r in self.rows)), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_workload(pkg, cells, order, v0):
@@ -109,6 +139,17 @@ def build_workload(pkg, cells, order, v0):
     dt = 0.1 * mesh.h_min() / (c0 * (2 * order + 1))
     mesh.set_physics(c0=c0, rho0=rho0, v0=v0, dt=dt)
     return model, cfg, mesh
+
+
+def measured_traffic(kernel_name, K):
+    """DRAM bytes per launch of the stage kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one launch, per element of the profiled mesh), scaled to K elements."""
+    p = ROOT / "profiles" / "r01_traffic.json"
+    try:
+        rec = json.loads(p.read_text())[kernel_name]
+        return rec["dram_bytes_per_element"] * K, rec
+    except Exception:
+        return None, None
 
 
 def alg_counts(mesh, v0_zero):
@@ -199,6 +240,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever libraries print (e.g. the NCCL version banner) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     pkg = graft.load_package()
     workload = f"cube n={args.cells} ({args.cells ** 3 * 6} tets) order {args.order} RK4"
     config = {"workload": workload, "cells": args.cells, "order": args.order, "v0": args.v0, "boundary": "absorbing",
@@ -219,7 +268,7 @@ def main():
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": wall}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -306,6 +355,7 @@ def main():
         gbs = bytes_stage * frac_work / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
         tfl = flops_stage * frac_work / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
         hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+        traffic, traffic_rec = measured_traffic(eng.kernel_name, K * frac_work)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -313,7 +363,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": state_bytes / args.steps,
                     "what": "dgb_set_state(pinned host) + dgb_run(steps) + dgb_get_state(pinned host), host clock"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
+                         "traffic_source": (traffic_rec or {}).get("source"),
                          "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6.65 TB/s",
                          "stage_kernel_ms": stage_ms, "alg_bytes_per_launch": bytes_stage * frac_work,
                          "fp64": {"achieved": tfl, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tfl / FP64_PEAK_TFLOPS,
@@ -324,7 +375,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
