@@ -69,7 +69,10 @@ struct WsCfg {
     static constexpr int NT = (NP + 7) / 8, NPP = NT * 8;    // node tiles (n of the MMA)
     static constexpr int KTQ = (NP + 3) / 4, KQ = KTQ * 4;   // k-tiles of a volume block, padded block length
     // lift k-tiles owned by each of the MMA roles D_0..2 (role r: [r*NSD, (r+1)*NSD)); role L owns the rest
-    static constexpr int NSD = P == 4 ? 3 : 2;
+#ifndef DGB_WS_NSD4
+#define DGB_WS_NSD4 3
+#endif
+    static constexpr int NSD = P == 4 ? DGB_WS_NSD4 : 2;
     // input row of one element (doubles): p / rho0 | c_0 | c_1 | c_2 | F_p / (rho0 c0^2) | F_vx | F_vy | F_vz
     static constexpr int OFF_P = 0, OFF_C = KQ, OFF_F = 4 * KQ;
     static constexpr int LDI = padTo8mod16(4 * KQ + 4 * NFL);
