@@ -233,6 +233,8 @@ def main():
     ap.add_argument("--v0", type=float, nargs=3, default=[0.0, 0.0, 0.0])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--overlap", type=int, default=None, help="halo exchange overlap mode 0/1/2 (default: the engine's)")
+    ap.add_argument("--sm-reserve", type=int, default=None, help="SMs left to the halo-exchange kernels during overlapped launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     args = ap.parse_args()
@@ -306,6 +308,10 @@ def main():
         eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
         if args.no_overlap:
             eng.set_option("overlap", 0)
+        if args.overlap is not None:
+            eng.set_option("overlap", args.overlap)
+        if args.sm_reserve is not None:
+            eng.set_option("sm_reserve", args.sm_reserve)
     else:
         eng = pkg.Engine(mesh)
     if args.kernel:

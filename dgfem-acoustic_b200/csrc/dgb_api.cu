@@ -128,7 +128,9 @@ struct dgb_handle {
     int stageEvUsed = 0;
     StageKernel generic, tiled, ws, active;
     StageKernel autoKernel() const { return ws.launch ? ws : tiled.launch ? tiled : generic; }
-    int overlap = 1;
+    int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
+    int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
+    bool recvPending = false;  // overlap 2: the halo exchange of the previous stage has not been waited for yet
     int timeStages = 1;
     // sources
     std::vector<int32_t> srcOff;
@@ -444,10 +446,13 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
 // ---------------------------------------------------------------------------------------------
 // time loop
 // ---------------------------------------------------------------------------------------------
+int overlapMode(const dgb_handle* h);
+
 void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     if (eEnd <= eBegin) return;
     A.eBegin = eBegin;
     A.eEnd = eEnd;
+    A.smReserve = (h->partitioned && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches only
     const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
     if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
     h->active.launch(h->M, A, h->stream);
@@ -475,7 +480,21 @@ void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
     NCCL_CHECK(nccl().GroupEnd());
 }
 
-// One stage = [border elements -> pack -> exchange on the comm stream] overlapped with [interior elements].
+// Effective overlap mode. Measured on B200 (config 5, profiles/r01w_scale_*.json): the persistent DMMA kernels pay more for a
+// second, small launch per stage (prologue, pipeline fill / drain, static tile lists) than the ~0.09 ms exchange costs, at 2, 4
+// and 8 GPUs alike, so they run one launch per stage and exchange afterwards; the light-weight generic kernel overlaps.
+int overlapMode(const dgb_handle* h) {
+    if (h->overlap >= 0) return h->overlap;
+    return h->active.launch == h->generic.launch ? 1 : 0;
+}
+
+// One stage of a partitioned run. Only the cut-adjacent ("border") elements read halo values, so the exchange of the values
+// produced by stage s can run beside the interior elements of stage s+1 (overlap 2):
+//   main stream : interior(s+1) | wait recv(s) | border(s+1) | pack(s+1)
+//   comm stream :   exchange(s) .............. |             |          | exchange(s+1) ...
+// The DMMA kernels are persistent (one CTA per SM, static tile lists), so the interior launch leaves `smReserve` SMs to the
+// NCCL kernels. Overlap 1 is the older order (border first, exchange beside the interior of the SAME stage): with the
+// persistent kernels its small border launch and the late CTAs behind the NCCL kernels cost more than the exchange it hides.
 void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
     const PartitionPlan& P = h->plan;
     if (!h->partitioned) {
@@ -483,7 +502,22 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
         return;
     }
     const int nSendEl = (int)P.sendElems.size();
-    if (h->overlap) {
+    const int overlap = overlapMode(h);
+    if (overlap == 2) {
+        launchStage(h, A, 0, P.Kinterior, true);
+        if (h->recvPending) {
+            CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
+            h->recvPending = false;
+        }
+        launchStage(h, A, P.Kinterior, P.Kown, false);
+        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        ++h->launches;
+        CUDA_CHECK(cudaEventRecord(h->evBorder, h->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(h->commStream, h->evBorder, 0));
+        exchangeHalo(h, produced, h->commStream);
+        CUDA_CHECK(cudaEventRecord(h->evRecv, h->commStream));
+        h->recvPending = true;
+    } else if (overlap == 1) {
         launchStage(h, A, P.Kinterior, P.Kown, false);
         launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
         ++h->launches;
@@ -498,6 +532,14 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
         launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
         ++h->launches;
         exchangeHalo(h, produced, h->stream);
+    }
+}
+
+// Closes the deferred exchange of overlap 2 (before anything but a stage launch touches the halo slots)
+void finishExchange(dgb_handle* h) {
+    if (h->recvPending) {
+        CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
+        h->recvPending = false;
     }
 }
 
@@ -524,6 +566,7 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
             ++h->probeCount;
             ++h->launches;
         }
+        if (!h->srcAmp.empty()) finishExchange(h);  // sources overwrite halo copies of U too: the exchange of the last stage must have landed
         for (size_t s = 0; s < h->srcAmp.size(); ++s)
             if (t < h->srcDur[s]) {  // solver.cpp:253-255, evaluated on the host in the reference's own expression
                 const double val = h->srcAmp[s] * sin(2 * M_PI * h->srcFreq[s] * t + h->srcPhase[s]);
@@ -544,6 +587,7 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
         A.yin = h->YB; A.yout = h->YA; A.mode = MODE_RK3; runStage(h, A, h->YA);
         A.yin = h->YA; A.yout = nullptr; A.mode = MODE_RK4; runStage(h, A, h->U);
     }
+    finishExchange(h);
     CUDA_CHECK(cudaEventRecord(h->evStop, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     CUDA_CHECK(cudaGetLastError());
@@ -779,7 +823,11 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
                 if (!h->ws.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no warp-specialised kernel for this dim/order/mean flow");
                 h->active = h->ws;
             } else h->active = h->autoKernel();
-        } else if (k == "overlap") h->overlap = value ? 1 : 0;
+        } else if (k == "overlap") {
+            if (value < -1 || value > 2) throw DgbException(DGB_ERR_ARG, "overlap must be -1 (automatic), 0, 1 or 2");
+            h->overlap = value;
+        }
+        else if (k == "sm_reserve") h->smReserve = std::max(0, value);
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;
         else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
     });

@@ -53,6 +53,7 @@ struct StageArgs {
     int eBegin, eEnd;    // element range of this launch
     int mode;
     double dt;
+    int smReserve;       // persistent kernels leave this many SMs free (halo exchange kernels running beside an interior launch)
 };
 
 // Returns a printable kernel name; launches on `stream`. kernelChoice: 0 auto, 1 generic, 2 tiled.

@@ -548,7 +548,7 @@ void launchTiledImpl(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
         configured = true;
     }
     const int nUnits = (nEl + 3) / 4;
-    const int grid = std::max(1, std::min(numSm, (nUnits + kWarps - 1) / kWarps));
+    const int grid = std::max(1, std::min(numSm - std::min(A.smReserve, numSm / 2), (nUnits + kWarps - 1) / kWarps));
     stageTiledKernel<P, FLOW><<<grid, kWarps * 32, smem, s>>>(M, A, nUnits);
 }
 

@@ -723,7 +723,7 @@ void launchWs(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
         configured = true;
     }
     const int nTiles = (nEl + kTileEl - 1) / kTileEl;
-    const int grid = std::max(1, std::min(numSm, nTiles));
+    const int grid = std::max(1, std::min(numSm - std::min(A.smReserve, numSm / 2), nTiles));
     stageWsKernel<P><<<grid, kThreadsWs, smem, s>>>(M, A, nTiles);
 }
 

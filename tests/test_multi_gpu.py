@@ -1,5 +1,5 @@
-"""Domain decomposition across GPUs: partitioned run == single-GPU run, with and without the
-interior/halo overlap. Needs >= 2 CUDA devices; one process per GPU, NCCL halo exchange."""
+"""Domain decomposition across GPUs: partitioned run == single-GPU run, for every halo-exchange overlap
+mode (0 none, 1 same stage, 2 next stage, -1 automatic), with and without mean flow (both DMMA kernels). Needs >= 2 CUDA devices; one process per GPU, NCCL halo exchange."""
 import subprocess
 import sys
 from pathlib import Path
@@ -20,7 +20,8 @@ def _device_count():
         return 0
 
 
-@pytest.mark.parametrize("world,cells,order,overlap,flow", [(2, 6, 4, 1, 1), (2, 6, 4, 0, 1), (2, 5, 2, 1, 1), (2, 6, 4, 1, 0), (2, 7, 4, 0, 0)])
+@pytest.mark.parametrize("world,cells,order,overlap,flow", [(2, 6, 4, 1, 1), (2, 6, 4, 0, 1), (2, 5, 2, 1, 1), (2, 6, 4, 1, 0), (2, 7, 4, 0, 0), (2, 6, 4, 2, 0), (2, 6, 4, 2, 1),
+                                                                (2, 5, 2, 2, 1), (2, 6, 4, -1, 0)])
 def test_partitioned_equals_single(tmp_path, world, cells, order, overlap, flow):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
