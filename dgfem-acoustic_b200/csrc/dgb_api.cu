@@ -9,6 +9,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dgb_internal.h"
@@ -119,6 +120,7 @@ struct dgb_handle {
     dgb_desc hd{};  // scalar members of the global desc
     int Kglobal = 0, Np = 0;
     bool partitioned = false;
+    int nranks = 1;
     PartitionPlan plan;
     double *U = nullptr, *ACC = nullptr, *YA = nullptr, *YB = nullptr;
     cudaStream_t stream = nullptr, commStream = nullptr;
@@ -300,6 +302,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         h->Kglobal = K;
         h->Np = Np;
         h->partitioned = nranks > 1;
+        h->nranks = nranks;
         if (h->partitioned) {
             h->plan = makePartitionPlan(K, Nf, d->elFId, d->fNbrElId, elPart, rank, nranks);
         } else {
@@ -622,6 +625,14 @@ int guarded(Fn fn) {
 }
 
 // host <-> device state transfer; identity layout on one GPU, gather/scatter by element when partitioned
+// Host threads of the gather / scatter loops: a fair share of the machine per rank, whatever OMP_NUM_THREADS says (torchrun
+// sets it to 1, which would make the host side of dgb_set_state / dgb_get_state the slowest part of a partitioned run).
+int hostThreads(const dgb_handle* h) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int share = (int)(hw ? hw : 8) / std::max(1, h->nranks);
+    return std::max(1, std::min(share, 16));
+}
+
 double* stagingBuffer(dgb_handle* h) {
     if (!h->hostStage) CUDA_CHECK(cudaMallocHost(&h->hostStage, (size_t)4 * h->M.stride * sizeof(double)));
     return h->hostStage;
@@ -638,11 +649,14 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
     double* stage = stagingBuffer(h);
     const int32_t* l2g = h->plan.localToGlobal.data();
     const int Ktot = h->M.Ktot;
-#pragma omp parallel for collapse(2) schedule(static)
-    for (int q = 0; q < 4; ++q)
+    const int nth = hostThreads(h);
+    // field by field: the copy of field q runs while field q+1 is gathered
+    for (int q = 0; q < 4; ++q) {
+#pragma omp parallel for schedule(static) num_threads(nth)
         for (int l = 0; l < Ktot; ++l)
             std::memcpy(stage + (size_t)q * S + (size_t)l * Np, u + q * Ng + (int64_t)l2g[l] * Np, Np * sizeof(double));
-    CUDA_CHECK(cudaMemcpyAsync(dst, stage, (size_t)4 * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)q * S, stage + (size_t)q * S, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
@@ -655,14 +669,23 @@ void stateToHost(dgb_handle* h, const double* src, double* u) {
         return;
     }
     double* stage = stagingBuffer(h);
-    CUDA_CHECK(cudaMemcpyAsync(stage, src, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
     const int32_t* l2g = h->plan.localToGlobal.data();
     const int Kown = h->M.Kown;
-#pragma omp parallel for collapse(2) schedule(static)
-    for (int q = 0; q < 4; ++q)
+    const int nth = hostThreads(h);
+    cudaEvent_t ev[4];
+    for (int q = 0; q < 4; ++q) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming));
+        CUDA_CHECK(cudaMemcpyAsync(stage + (size_t)q * S, src + (size_t)q * S, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaEventRecord(ev[q], h->stream));
+    }
+    // field by field: field q is scattered while field q+1 is still in flight
+    for (int q = 0; q < 4; ++q) {
+        CUDA_CHECK(cudaEventSynchronize(ev[q]));
+        cudaEventDestroy(ev[q]);
+#pragma omp parallel for schedule(static) num_threads(nth)
         for (int l = 0; l < Kown; ++l)  // owned elements only
             std::memcpy(u + q * Ng + (int64_t)l2g[l] * Np, stage + (size_t)q * S + (size_t)l * Np, Np * sizeof(double));
+    }
 }
 
 // global DG node index -> local (or -1); halo copies included when withHalo
