@@ -92,6 +92,11 @@ struct WsCfg {
         return k < 32 ? (k >> 3) * NFP + (k & 7) : ((k - 32) / (NFP - 8)) * NFP + 8 + (k - 32) % (NFP - 8);
     }
     static_assert(NFL % 4 == 0, "lift contraction length must be a multiple of 4");
+    // everything the CTA asks for: rings + mbarriers + face-node table + face-pairing byte maps
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 32 * 8 + NFL * 4 + kMaxMapsWs * NFP;
+    // 196 KB carve-out minus the 1 KB the system reserves per CTA: above it the SM falls back to the 228 KB carve-out and
+    // the kernel loses half of its L1 (measured: 2.65 -> 3.15 ms per stage, profiles/r01_ws_ablation.txt)
+    static_assert(SMEM_BYTES <= 195 * 1024, "shared memory must stay under the 196 KB carve-out");
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -714,7 +719,8 @@ void launchWs(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     if (nEl <= 0) return;
     static int numSm = 0;
     static bool configured = false;
-    const size_t smem = (size_t)C::SMEM_DOUBLES * sizeof(double) + kNumBars * sizeof(unsigned long long) + C::NFL * sizeof(int) + kMaxMapsWs * C::NFP;
+    static_assert(kNumBars <= 32, "barrier block");
+    const size_t smem = C::SMEM_BYTES;
     if (!configured) {
         int dev = 0;
         cudaGetDevice(&dev);

@@ -216,6 +216,15 @@ def test_error_behaviour(pkg, mesh_dir):
         eng.run(7, 0.0, 1)  # unknown integrator
     with pytest.raises(pkg.DgbError):
         eng.set_option("no_such_option", 1)
+    with pytest.raises(pkg.DgbError):
+        eng.set_option("kernel", 3)  # no warp-specialised kernel for a 1D mesh
+    with pytest.raises(pkg.DgbError):
+        eng.set_option("overlap", 3)
+    flow = build_mesh(pkg, mesh_dir, "cube:2", 4, (10.0, 0.0, 0.0))
+    eng2 = pkg.Engine(flow)
+    assert "tiled" in eng2.kernel_name  # mean flow: the warp-specialised kernel is not offered
+    with pytest.raises(pkg.DgbError):
+        eng2.set_option("kernel", 3)
 
 
 KERNEL_IDS = {"generic": 1, "tiled": 2, "ws": 3}
