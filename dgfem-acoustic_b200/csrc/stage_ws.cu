@@ -195,19 +195,31 @@ __device__ __forceinline__ WsBars wsBars(const WsSmem& sm) {
     return {b, b + kInStages, b + 2 * kInStages, b + 2 * kInStages + 2 * kOutStages, b + 2 * kInStages + 3 * kOutStages};
 }
 constexpr int kNumBars = 2 * kInStages + 4 * kOutStages;
-// Tiles of a CTA: interleaved over the grid (tile = blockIdx + it * gridDim), or -- DGB_WS_CONTIG -- one contiguous range
-// per CTA, which keeps the neighbour elements of the next tiles in this SM's L1.
+// Tiles of a CTA: chunks of DGB_WS_CHUNK consecutive tiles, the chunks interleaved over the grid (chunk j goes to CTA
+// j % gridDim). Interleaving keeps the SMs on neighbouring parts of the mesh at the same time (L2 hits for the neighbour
+// traces; one contiguous range per CTA measured 12 % slower); consecutive tiles on one SM find their neighbours in its L1.
+#ifndef DGB_WS_CHUNK
+#define DGB_WS_CHUNK 1
+#endif
 struct TileMap {
-    int first, step, count;  // first tile, tile stride, number of tiles
+    int b, G, count;  // CTA, grid size, number of tiles of this CTA
+    // element offset (relative to the first element of the launch) of the it-th tile of this CTA; may run past the end
+    __device__ __forceinline__ int elem(int it) const {
+        constexpr int c = DGB_WS_CHUNK;
+        return (c == 1 ? it * G + b : ((it / c) * G + b) * c + it % c) * kTileEl;
+    }
 };
 __device__ __forceinline__ TileMap tileMap(int nTiles) {
+    constexpr int c = DGB_WS_CHUNK;
     const int b = (int)blockIdx.x, G = (int)gridDim.x;
-#ifdef DGB_WS_CONTIG
-    const int Q = nTiles / G, R = nTiles - Q * G;
-    return {b * Q + min(b, R), 1, Q + (b < R ? 1 : 0)};
-#else
-    return {b, G, b < nTiles ? (nTiles - b + G - 1) / G : 0};
-#endif
+    const int nChunks = (nTiles + c - 1) / c;
+    int count = 0;
+    if (b < nChunks) {
+        const int mine = (nChunks - b + G - 1) / G;          // chunks of this CTA
+        const int last = b + (mine - 1) * G;                 // its last chunk may be a partial one
+        count = (mine - 1) * c + min(c, nTiles - last * c);
+    }
+    return {b, G, count};
 }
 // position and phase parity in an N-deep ring (N need not be a power of two)
 template <int N>
@@ -409,9 +421,8 @@ __device__ __forceinline__ void frontWarp(const DeviceMesh& M, const StageArgs& 
 
     const WsBars bar = wsBars(sm);
     const TileMap tm = tileMap((A.eEnd - A.eBegin + kTileEl - 1) / kTileEl);
-    const int eStep = tm.step * kTileEl;
     const int eLast = A.eEnd - 1;
-    const int eFirst = A.eBegin + tm.first * kTileEl + s;
+    auto elemOf = [&](int it) { return A.eBegin + tm.elem(it) + s; };  // element s of the it-th tile of this CTA
 
     // Face metadata of element e (clamped: rows past the end of the range are computed on a copy of the last element and
     // never stored)
@@ -518,7 +529,6 @@ __device__ __forceinline__ void frontWarp(const DeviceMesh& M, const StageArgs& 
     // Prefetch: own values / geometry kOwnAhead tiles ahead in the cp.async rings, traces two tiles ahead in two register
     // sets. The loop is unrolled by two so that each set keeps its registers (even / odd tiles): a rotating copy would make
     // the compiler wait for the loads it has just issued.
-    int eIt = eFirst;  // element of the tile in hand
     Ring<kInStages> in;
     int it = 0;
     auto step = [&](int& flagsX, int& nbrX, double (&trX)[2][4], int& flagsP, int& nbrP) {
@@ -533,29 +543,28 @@ __device__ __forceinline__ void frontWarp(const DeviceMesh& M, const StageArgs& 
         __syncwarp();
         if (lane == 0) mbarArrive(&bar.full[in.b]);
         // refill: own values of tile it + kOwnAhead, traces of tile it + 2 (same register set), face metadata of tile it + 3
-        issueOwn(eIt + kOwnAhead * eStep, it + kOwnAhead);
+        issueOwn(elemOf(it + kOwnAhead), it + kOwnAhead);
         asm volatile("cp.async.commit_group;" ::: "memory");
         flagsX = flagsP; nbrX = nbrP;
 #ifndef DGB_WS_NOTRACES
-        loadTraces(eIt + 2 * eStep, flagsX, nbrX, trX);
+        loadTraces(elemOf(it + 2), flagsX, nbrX, trX);
 #endif
-        loadMeta(eIt + 3 * eStep, flagsP, nbrP);
-        eIt += eStep;
+        loadMeta(elemOf(it + 3), flagsP, nbrP);
         in.next();
         ++it;
     };
     int flagsA, nbrA, flagsB, nbrB, flagsP, nbrP;
     double trA[2][4], trB[2][4];
-    loadMeta(eFirst, flagsA, nbrA);
-    loadMeta(eFirst + eStep, flagsB, nbrB);
+    loadMeta(elemOf(0), flagsA, nbrA);
+    loadMeta(elemOf(1), flagsB, nbrB);
 #pragma unroll
     for (int d = 0; d < kOwnAhead; ++d) {
-        issueOwn(eFirst + d * eStep, d);
+        issueOwn(elemOf(d), d);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    loadTraces(eFirst, flagsA, nbrA, trA);
-    loadTraces(eFirst + eStep, flagsB, nbrB, trB);
-    loadMeta(eFirst + 2 * eStep, flagsP, nbrP);
+    loadTraces(elemOf(0), flagsA, nbrA, trA);
+    loadTraces(elemOf(1), flagsB, nbrB, trB);
+    loadMeta(elemOf(2), flagsP, nbrP);
     while (it < nIt) {
         step(flagsA, nbrA, trA, flagsP, nbrP);
         if (it < nIt) step(flagsB, nbrB, trB, flagsP, nbrP);
@@ -602,11 +611,10 @@ __device__ __forceinline__ void backWarpImpl(const DeviceMesh& M, const StageArg
     double* const accP = A.acc + q * S;
     double* const youtP = A.yout + q * S;
     const TileMap tm = tileMap((A.eEnd - A.eBegin + kTileEl - 1) / kTileEl);
-    const int eStep = tm.step * kTileEl;
-    int e0 = A.eBegin + tm.first * kTileEl;
 
     Ring<kOutStages> ou;
-    for (int it = 0; it < nIt; ++it, e0 += eStep, ou.next()) {
+    for (int it = 0; it < nIt; ++it, ou.next()) {
+        const int e0 = A.eBegin + tm.elem(it);
         const int nVal = min(kTileEl, A.eEnd - e0) * NP;  // valid values of this tile
         const size_t base = (size_t)e0 * NP + lane;
         double uv[NV], av[NV];
