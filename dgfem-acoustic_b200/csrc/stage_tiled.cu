@@ -30,7 +30,10 @@ namespace dgb {
 namespace {
 
 constexpr int kMaxMaps = 64;
-constexpr int kWarps = 8;
+#ifndef DGB_TILED_WARPS
+#define DGB_TILED_WARPS 8
+#endif
+constexpr int kWarps = DGB_TILED_WARPS;
 
 // Optional per-phase cycle counters (development aid): compile with -DDGB_TILED_PHASE_TIMERS, read with
 // dgbTiledPhaseTimers(). Off in the product build.

@@ -1,12 +1,14 @@
-"""Small RK4 run through the tiled kernel for compute-sanitizer (memcheck / racecheck)."""
+"""Small RK4 + Euler runs through the DMMA kernels for compute-sanitizer (memcheck / racecheck):
+python profiles/sanitize.py [order] [flow: 0 = zero mean flow -> warp-specialised kernel, 1 = mean flow -> tiled kernel]"""
 import sys
 import numpy as np
 sys.path.insert(0, "/root/repo")
 import __graft_entry__ as g
 pkg = g.load_package()
 order = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+flow = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 mesh = pkg.Mesh(pkg.Model.make_cube(3, -10.0, 10.0, order), pkg.Config())
-mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0), dt=1e-5)
+mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0) if flow else (0.0, 0.0, 0.0), dt=1e-5)
 b = np.nonzero(mesh.fIsBoundary)[0]; mesh.fBC[b[::2]] = 1
 eng = pkg.Engine(mesh)
 eng.set_state(np.random.default_rng(0).standard_normal((4, mesh.N)))
