@@ -287,3 +287,19 @@ def test_ws_kernel_deep_rings(pkg, mesh_dir):
     b = eng.eval_rhs(u)
     for q in range(4):
         assert rel_l2(a[q], b[q]) < 1e-12
+
+
+def test_ws_kernel_is_deterministic(pkg, mesh_dir):
+    """The warp-specialised kernel hands tiles between warp roles through shared-memory rings and mbarriers; a missed
+    ordering would show up as run-to-run differences. Same input, same launch configuration -> bit-identical results."""
+    mesh = build_mesh(pkg, mesh_dir, "cube:12", 4, (0.0, 0.0, 0.0))  # 10 368 tets = 1 296 tiles, ~9 per CTA
+    u0 = np.random.default_rng(17).standard_normal((4, mesh.N))
+    eng = pkg.Engine(mesh)
+    assert "ws" in eng.kernel_name
+    runs = []
+    for _ in range(3):
+        eng.set_state(u0)
+        eng.run(pkg.RUNGE_KUTTA, 0.0, 6)
+        runs.append(eng.get_state().copy())
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    assert np.isfinite(runs[0]).all()
