@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--v0", type=float, nargs=3, default=[0.0, 0.0, 0.0])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA")
+    ap.add_argument("--partitioner", default="rcb", choices=["rcb", "metis"], help="element partition for --gpus > 1")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--overlap", type=int, default=None, help="halo exchange overlap mode 0/1/2 (default: the engine's)")
     ap.add_argument("--sm-reserve", type=int, default=None, help="SMs left to the halo-exchange kernels during overlapped launches")
@@ -253,7 +254,7 @@ def main():
     pkg = graft.load_package()
     workload = f"cube n={args.cells} ({args.cells ** 3 * 6} tets) order {args.order} RK4"
     config = {"workload": workload, "cells": args.cells, "order": args.order, "v0": args.v0, "boundary": "absorbing",
-              "l2": "inputs larger than L2 (state arrays of 1.6 GB each)", "partition": "rcb" if world > 1 else "none"}
+              "l2": "inputs larger than L2 (state arrays of 1.6 GB each)", "partition": args.partitioner if world > 1 else "none"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -300,7 +301,10 @@ def main():
     if world > 1:
         import ctypes as C
         part = np.zeros(K, dtype=np.int32)
-        assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        if args.partitioner == "metis":
+            assert pkg.load_front().dgf_partition_metis(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32)), None) == 0
+        else:
+            assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8, device="cuda")

@@ -82,6 +82,9 @@ int dgf_write_views(const char* path, const dgf_model* model, const dgf_mesh* me
 /* ---- domain decomposition, host-side planning shared with the engine ---------------- */
 /* recursive coordinate bisection of the element centroids into nparts parts (balanced to +-1 element) */
 int dgf_partition_rcb(const dgf_mesh* mesh, int nparts, int32_t* elPart /* [K] */);
+/* METIS k-way partition of the element dual graph (Gmsh's own partitioner is METIS as well); edgeCut (optional) = number of cut
+   faces. Returns 0, -1 on failure, -2 if the library was built without METIS (libmetis_static.a of the CUDA toolkit). */
+int dgf_partition_metis(const dgf_mesh* mesh, int nparts, int32_t* elPart /* [K] */, int64_t* edgeCut);
 typedef struct dgf_plan dgf_plan;
 dgf_plan* dgf_plan_create(const dgf_mesh* mesh, const int32_t* elPart, int rank, int nranks);
 void dgf_plan_free(dgf_plan* plan);

@@ -165,3 +165,25 @@ def test_rcb_partition_is_balanced(pkg):
         assert pkg.load_front().dgf_partition_rcb(mesh.h, nparts, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
         counts = np.bincount(part, minlength=nparts)
         assert counts.max() - counts.min() <= 1 and len(counts) == nparts
+
+
+def test_metis_partition_balanced_and_connected(pkg, mesh_dir):
+    """METIS k-way partition of the element dual graph: every part is used, balance within METIS' 3 %
+    (+1 element), the reported edge cut equals the number of faces between parts, and it does not lose to RCB on a shipped
+    unstructured mesh."""
+    front = pkg.load_front()
+    for mesh in (pkg.Mesh(pkg.Model.make_cube(6, -10.0, 10.0, 1), pkg.Config()), pkg.Mesh(pkg.Model.open_msh(mesh_dir / "sphere.msh", 1), pkg.Config())):
+        inner = mesh.fNbrElId[:, 1] >= 0
+        for nparts in (1, 2, 4, 8):
+            part = np.zeros(mesh.K, dtype=np.int32)
+            cut = C.c_int64(-1)
+            assert front.dgf_partition_metis(mesh.h, nparts, part.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(cut)) == 0
+            counts = np.bincount(part, minlength=nparts)
+            assert len(counts) == nparts and counts.min() > 0
+            assert counts.max() <= 1.03 * mesh.K / nparts + 1
+            cut_faces = int((part[mesh.fNbrElId[inner, 0]] != part[mesh.fNbrElId[inner, 1]]).sum())
+            assert cut.value == cut_faces
+            rcb = np.zeros(mesh.K, dtype=np.int32)
+            assert front.dgf_partition_rcb(mesh.h, nparts, rcb.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+            rcb_cut = int((rcb[mesh.fNbrElId[inner, 0]] != rcb[mesh.fNbrElId[inner, 1]]).sum())
+            assert cut_faces <= 1.15 * rcb_cut + 8, (nparts, cut_faces, rcb_cut)

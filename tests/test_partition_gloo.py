@@ -38,7 +38,7 @@ def _plan(pkg, mesh, part, rank, world):
     return dict(kown=kown, kint=kint, khalo=khalo, l2g=l2g, peers=peers[:npeers], roff=roff, soff=soff, send=send[:nsend])
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, partitioner):
     import torch
     import torch.distributed as dist
 
@@ -53,7 +53,10 @@ def _worker(rank, world, port, out_dir):
     mesh = pkg.Mesh(pkg.Model.make_cube(3, -10.0, 10.0, 2), pkg.Config())
     mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0), dt=1e-4)
     part = np.zeros(mesh.K, dtype=np.int32)
-    assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    if partitioner == "metis":
+        assert pkg.load_front().dgf_partition_metis(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32)), None) == 0
+    else:
+        assert pkg.load_front().dgf_partition_rcb(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32))) == 0
     plan = _plan(pkg, mesh, part, rank, world)
     Np, N = mesh.Np, mesh.N
     l2g, kown = plan["l2g"], plan["kown"]
@@ -100,11 +103,11 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_halo_plan_over_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,partitioner", [(2, "rcb"), (2, "metis"), (3, "metis")])
+def test_halo_plan_over_gloo(tmp_path, world, partitioner):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(world, 29731, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29731 + world + (7 if partitioner == "metis" else 0), str(tmp_path), partitioner), nprocs=world, join=True)
     sizes = [np.load(tmp_path / f"ok{r}.npy") for r in range(world)]
     assert sum(int(s[0]) for s in sizes) == 3 ** 3 * 6
     assert all(int(s[1]) > 0 for s in sizes)
