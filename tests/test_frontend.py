@@ -187,3 +187,53 @@ def test_metis_partition_balanced_and_connected(pkg, mesh_dir):
             assert front.dgf_partition_rcb(mesh.h, nparts, rcb.ctypes.data_as(C.POINTER(C.c_int32))) == 0
             rcb_cut = int((rcb[mesh.fNbrElId[inner, 0]] != rcb[mesh.fNbrElId[inner, 1]]).sum())
             assert cut_faces <= 1.15 * rcb_cut + 8, (nparts, cut_faces, rcb_cut)
+
+
+def test_view_writer_round_trip(pkg, mesh_dir, tmp_path):
+    """dgf_write_views appends $ElementNodeData views named Pressure / Density / Velocity (solver.cpp:185-188, 226-238, 289-291):
+    one block per view and snapshot, element tags of the mesh, Np values per element; density = p / c0^2 (solver.cpp:230)."""
+    model = pkg.Model.open_msh(mesh_dir / "square.msh", 2)
+    cfg = pkg.Config()
+    cfg.c.c0 = 343.0
+    mesh = pkg.Mesh(model, cfg)
+    rng = np.random.default_rng(2)
+    snaps = rng.standard_normal((2, 4, mesh.N))
+    steps = np.array([0, 10], dtype=np.int32)
+    times = np.array([0.0, 1e-3])
+    out = tmp_path / "views.msh"
+    rc = pkg.load_front().dgf_write_views(str(out).encode(), model.h, mesh.h, C.byref(cfg.c), 2, steps.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          times.ctypes.data_as(C.POINTER(C.c_double)), snaps.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    text = out.read_text().split("\n")
+    assert text[0] == "$MeshFormat" and text[1].split()[:2] == ["4", "0"]
+    blocks, i = [], 0
+    while i < len(text):
+        if text[i] == "$ElementNodeData":
+            assert text[i + 1] == "1"
+            name = text[i + 2].strip('"')
+            assert text[i + 3] == "1"
+            t = float(text[i + 4])
+            assert text[i + 5] == "3"
+            step, ncomp, nel = int(text[i + 6]), int(text[i + 7]), int(text[i + 8])
+            rows = [text[i + 9 + k].split() for k in range(nel)]
+            assert text[i + 9 + nel] == "$EndElementNodeData"
+            blocks.append((name, t, step, ncomp, rows))
+            i += 10 + nel
+        else:
+            i += 1
+    assert [(b[0], b[2]) for b in blocks] == [("Pressure", 0), ("Pressure", 10), ("Density", 0), ("Density", 10), ("Velocity", 0), ("Velocity", 10)]
+    tags = mesh.el_tags if hasattr(mesh, "el_tags") else None
+    for name, t, step, ncomp, rows in blocks:
+        s_idx = 0 if step == 0 else 1
+        assert t == times[s_idx] and len(rows) == mesh.K and ncomp == (3 if name == "Velocity" else 1)
+        vals = np.array([[float(x) for x in r[2:]] for r in rows])
+        assert all(int(r[1]) == mesh.Np for r in rows)
+        if tags is not None:
+            assert [int(r[0]) for r in rows] == list(tags)
+        U = snaps[s_idx].reshape(4, mesh.K, mesh.Np)
+        if name == "Pressure":
+            np.testing.assert_allclose(vals, U[0], rtol=1e-15)
+        elif name == "Density":
+            np.testing.assert_allclose(vals, U[0] / 343.0 ** 2, rtol=1e-14)
+        else:
+            np.testing.assert_allclose(vals.reshape(mesh.K, mesh.Np, 3), np.moveaxis(U[1:], 0, -1), rtol=1e-15)
