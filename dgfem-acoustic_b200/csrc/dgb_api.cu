@@ -133,6 +133,11 @@ struct dgb_handle {
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
     bool recvPending = false;  // overlap 2: the halo exchange of the previous stage has not been waited for yet
+    // CUDA graph of one RK4 step (4 stage launches) for launch-bound runs: small meshes on one GPU, no sources, no probes
+    int useGraph = -1;         // -1 automatic, 0 never, 1 whenever possible
+    cudaGraphExec_t stepGraph = nullptr;
+    double stepGraphDt = 0;
+    StageLaunchFn stepGraphKernel = nullptr;
     int timeStages = 1;
     // sources
     std::vector<int32_t> srcOff;
@@ -161,6 +166,7 @@ void freeHandle(dgb_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
     if (h->comm) nccl().CommDestroy(h->comm);
+    if (h->stepGraph) cudaGraphExecDestroy(h->stepGraph);
     if (h->hostStage) cudaFreeHost(h->hostStage);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
@@ -563,7 +569,44 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
     }
     h->stageEvUsed = 0;
     CUDA_CHECK(cudaEventRecord(h->evStart, h->stream));
-    for (int step = 0; step < nsteps; ++step, t += dt) {
+    // Launch-bound case (the reference's own 2D configs: a stage kernel of a few microseconds, 4 000 launches per run): the
+    // four stage launches of an RK4 step are captured once into a CUDA graph and replayed. The first step always runs
+    // eagerly (kernel attributes are set on first use), t accumulates exactly as in the eager loop (solver.cpp:216).
+    const bool graphable = !h->partitioned && h->ownStream && integrator == DGB_RUNGE_KUTTA && h->srcAmp.empty() && h->nprobe == 0 &&
+                           nsteps >= 4 && (h->useGraph == 1 || (h->useGraph < 0 && (int64_t)h->M.Kown * h->Np <= (1 << 18)));
+    int step0 = 0;
+    if (graphable) {
+        auto stages = [&](bool timed) {
+            StageArgs A{};
+            A.u = h->U; A.acc = h->ACC; A.dt = dt;
+            A.yin = h->U;  A.yout = h->YA; A.mode = MODE_RK1; launchStage(h, A, 0, h->M.Kown, timed);
+            A.yin = h->YA; A.yout = h->YB; A.mode = MODE_RK2; launchStage(h, A, 0, h->M.Kown, timed);
+            A.yin = h->YB; A.yout = h->YA; A.mode = MODE_RK3; launchStage(h, A, 0, h->M.Kown, timed);
+            A.yin = h->YA; A.yout = nullptr; A.mode = MODE_RK4; launchStage(h, A, 0, h->M.Kown, timed);
+        };
+        stages(true);  // step 0, eager (and timed: dgb_last_stage_kernel_ms)
+        t += dt;
+        step0 = 1;
+        if (!h->stepGraph || h->stepGraphDt != dt || h->stepGraphKernel != h->active.launch) {
+            if (h->stepGraph) { cudaGraphExecDestroy(h->stepGraph); h->stepGraph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const int64_t launchesBefore = h->launches;
+            CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            stages(false);
+            CUDA_CHECK(cudaStreamEndCapture(h->stream, &graph));
+            h->launches = launchesBefore;  // captured, not launched
+            CUDA_CHECK(cudaGraphInstantiate(&h->stepGraph, graph, 0));
+            cudaGraphDestroy(graph);
+            h->stepGraphDt = dt;
+            h->stepGraphKernel = h->active.launch;
+        }
+        for (int step = step0; step < nsteps; ++step, t += dt) {
+            CUDA_CHECK(cudaGraphLaunch(h->stepGraph, h->stream));
+            h->launches += 4;
+        }
+        step0 = nsteps;
+    }
+    for (int step = step0; step < nsteps; ++step, t += dt) {
         if (h->nprobe > 0) {
             launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
             ++h->probeCount;
@@ -851,6 +894,7 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             h->overlap = value;
         }
         else if (k == "sm_reserve") h->smReserve = std::max(0, value);
+        else if (k == "graph") h->useGraph = value < 0 ? -1 : (value ? 1 : 0);
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;
         else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
     });

@@ -303,3 +303,23 @@ def test_ws_kernel_is_deterministic(pkg, mesh_dir):
         runs.append(eng.get_state().copy())
     assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
     assert np.isfinite(runs[0]).all()
+
+
+@pytest.mark.parametrize("name,order", [("square.msh", 2), ("cube:3", 4)])
+def test_cuda_graph_of_a_step_equals_eager_launches(pkg, mesh_dir, name, order):
+    """Launch-bound runs replay one captured RK4 step (dgb_set_option("graph")): same kernels, same arguments -> bit-identical
+    results and the same accumulated end time as the eager loop; the launch count still counts every stage."""
+    mesh = build_mesh(pkg, mesh_dir, name, order, (0.0, 0.0, 0.0))
+    u0 = smooth_state(mesh)
+    out, tend, launches = {}, {}, {}
+    for mode in (0, 1):
+        eng = pkg.Engine(mesh)
+        eng.set_option("graph", mode)
+        eng.set_state(u0)
+        tend[mode] = eng.run(pkg.RUNGE_KUTTA, 0.0, 40)
+        tend[mode] = eng.run(pkg.RUNGE_KUTTA, tend[mode], 25)  # second call re-uses the instantiated graph
+        out[mode] = eng.get_state().copy()
+        launches[mode] = eng.launch_count
+        eng.close()
+    assert np.array_equal(out[0], out[1])
+    assert tend[0] == tend[1] and launches[0] == launches[1] == 4 * 65
