@@ -51,6 +51,7 @@ class DgfConfig(C.Structure):
         ("nSources", C.c_int32), ("sources", (C.c_double * 9) * 64),
         ("nInit", C.c_int32), ("initConditions", (C.c_double * 6) * 32),
         ("nPhysBC", C.c_int32), ("physBCTag", C.c_int32 * 64), ("physBCType", C.c_int32 * 64),
+        ("nReceivers", C.c_int32), ("receivers", (C.c_double * 3) * 64), ("receiverFile", C.c_char * 512),
     ]
 
 
@@ -99,6 +100,9 @@ def load_front():
     lib.dgf_source_nodes.argtypes = [C.c_void_p, C.POINTER(DgfConfig), c_int32_p, c_int32_p]
     lib.dgf_time_loop.argtypes = [C.POINTER(DgfConfig), c_int32_p, C.c_int, C.POINTER(C.c_int)]
     lib.dgf_nearest_node.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    lib.dgf_locate_point.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_double_p, c_double_p, C.POINTER(C.c_int)]
+    lib.dgf_write_receivers.argtypes = [C.c_char_p, C.c_int, c_double_p, C.c_int, C.c_double, C.c_double, c_double_p]
+    lib.dgf_write_wav.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p]
     lib.dgf_write_views.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(DgfConfig), C.c_int, c_int32_p,
                                     c_double_p, c_double_p]
     _front = lib
@@ -126,6 +130,16 @@ class Config:
         for k, v in enumerate([pole, x, y, z, size, amp, freq, phase, duration]):
             self.c.sources[i][k] = v
         self.c.nSources = i + 1
+
+    @property
+    def receivers(self):
+        return [list(self.c.receivers[i]) for i in range(self.c.nReceivers)]
+
+    def add_receiver(self, x, y, z):
+        i = self.c.nReceivers
+        for k, v in enumerate([x, y, z]):
+            self.c.receivers[i][k] = v
+        self.c.nReceivers = i + 1
 
     def add_initial_condition(self, x, y, z, size, amp):
         i = self.c.nInit
@@ -255,6 +269,27 @@ class Mesh:
     def nearest_node(self, x, y, z) -> int:
         return load_front().dgf_nearest_node(self.h, float(x), float(y), float(z))
 
+    def locate_point(self, x, y, z):
+        """(element id, Lagrange weights [Np], parametric coordinates [3], outside flag) of a point (receivers)."""
+        w = np.zeros(self.Np, dtype=np.float64)
+        uvw = np.zeros(3, dtype=np.float64)
+        outside = C.c_int(0)
+        el = load_front().dgf_locate_point(self.h, float(x), float(y), float(z), _as(c_double_p, w), _as(c_double_p, uvw), C.byref(outside))
+        if el < 0:
+            raise FrontError(load_front().dgf_last_error().decode())
+        return el, w, uvw, bool(outside.value)
+
+    def locate_receivers(self, points):
+        """(el [n], weights [n][Np]) for dgb_set_receivers; points outside the mesh raise."""
+        els, ws = [], []
+        for pt in points:
+            el, w, _, outside = self.locate_point(*pt)
+            if outside:
+                raise FrontError(f"receiver {tuple(pt)} lies outside the mesh")
+            els.append(el)
+            ws.append(w)
+        return np.array(els, dtype=np.int32), np.array(ws, dtype=np.float64).reshape(len(els), self.Np)
+
     def h_min(self) -> float:
         """Smallest inscribed-sphere-like length d*|el|/|faces| (used to pick a CFL-stable dt in tests/bench)."""
         det_e = np.abs(self.elJacobianDet[:, 0])
@@ -301,6 +336,8 @@ def load_dgb():
     lib.dgb_set_sources.argtypes = [C.c_void_p, C.c_int, c_int32_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p]
     lib.dgb_set_probes.argtypes = [C.c_void_p, C.c_int, c_int32_p]
     lib.dgb_get_probes.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int)]
+    lib.dgb_set_receivers.argtypes = [C.c_void_p, C.c_int, c_int32_p, c_double_p]
+    lib.dgb_get_receivers.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int)]
     lib.dgb_run.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, c_double_p]
     lib.dgb_eval_rhs.argtypes = [C.c_void_p, c_double_p, c_double_p]
     lib.dgb_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -380,6 +417,19 @@ class Engine:
         out = np.zeros((capacity_steps, self.nprobe, 4), dtype=np.float64)
         n = C.c_int(0)
         self._check(self.lib.dgb_get_probes(self.h, _as(c_double_p, out), capacity_steps, C.byref(n)))
+        return out[: n.value]
+
+    def set_receivers(self, el, weights):
+        el = np.ascontiguousarray(el, dtype=np.int32)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (len(el), self.mesh.Np)
+        self.nrecv = len(el)
+        self._check(self.lib.dgb_set_receivers(self.h, len(el), _as(c_int32_p, el), _as(c_double_p, w)))
+
+    def get_receivers(self, capacity_steps):
+        out = np.zeros((capacity_steps, self.nrecv, 4), dtype=np.float64)
+        n = C.c_int(0)
+        self._check(self.lib.dgb_get_receivers(self.h, _as(c_double_p, out), capacity_steps, C.byref(n)))
         return out[: n.value]
 
     def run(self, integrator, t_start, nsteps):

@@ -148,6 +148,11 @@ struct dgb_handle {
     int32_t* dProbeIdx = nullptr;
     double* dProbeRec = nullptr;
     int probeCap = 0, probeCount = 0;
+    // receivers (interpolated inside an element)
+    int nrecv = 0;
+    int32_t* dRecvEl = nullptr;
+    double *dRecvW = nullptr, *dRecvRec = nullptr;
+    int recvCap = 0, recvCount = 0;
     bool stateSet = false;
     double lastRunMs = 0, lastStageMs = 0;
     int64_t launches = 0;
@@ -171,7 +176,7 @@ void freeHandle(dgb_handle* h) {
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
-    F(h->dSrcIdx); F(h->dProbeIdx); F(h->dProbeRec); F(h->sendBuf); F(h->recvBuf); F(h->dSendElems);
+    F(h->dSrcIdx); F(h->dProbeIdx); F(h->dProbeRec); F(h->dRecvEl); F(h->dRecvW); F(h->dRecvRec); F(h->sendBuf); F(h->recvBuf); F(h->dSendElems);
     for (auto e : h->stageEv) cudaEventDestroy(e);
     for (auto e : {h->evStart, h->evStop, h->evBorder, h->evRecv}) if (e) cudaEventDestroy(e);
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
@@ -567,12 +572,21 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
         h->dProbeRec = nb;
         h->probeCap = cap;
     }
+    if (h->nrecv > 0 && h->recvCount + nsteps > h->recvCap) {
+        const int cap = std::max(h->recvCount + nsteps, 2 * h->recvCap);
+        double* nb = devAlloc<double>((size_t)cap * h->nrecv * 4);
+        if (h->recvCount) CUDA_CHECK(cudaMemcpyAsync(nb, h->dRecvRec, (size_t)h->recvCount * h->nrecv * 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->dRecvRec) cudaFree(h->dRecvRec);
+        h->dRecvRec = nb;
+        h->recvCap = cap;
+    }
     h->stageEvUsed = 0;
     CUDA_CHECK(cudaEventRecord(h->evStart, h->stream));
     // Launch-bound case (the reference's own 2D configs: a stage kernel of a few microseconds, 4 000 launches per run): the
     // four stage launches of an RK4 step are captured once into a CUDA graph and replayed. The first step always runs
     // eagerly (kernel attributes are set on first use), t accumulates exactly as in the eager loop (solver.cpp:216).
-    const bool graphable = !h->partitioned && h->ownStream && integrator == DGB_RUNGE_KUTTA && h->srcAmp.empty() && h->nprobe == 0 &&
+    const bool graphable = !h->partitioned && h->ownStream && integrator == DGB_RUNGE_KUTTA && h->srcAmp.empty() && h->nprobe == 0 && h->nrecv == 0 &&
                            nsteps >= 4 && (h->useGraph == 1 || (h->useGraph < 0 && (int64_t)h->M.Kown * h->Np <= (1 << 18)));
     int step0 = 0;
     if (graphable) {
@@ -610,6 +624,11 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
         if (h->nprobe > 0) {
             launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
             ++h->probeCount;
+            ++h->launches;
+        }
+        if (h->nrecv > 0) {  // owned elements only: no halo value is read
+            launchGatherReceivers(h->U, h->M.stride, h->Np, h->dRecvEl, h->dRecvW, h->nrecv, h->dRecvRec + (size_t)h->recvCount * h->nrecv * 4, h->stream);
+            ++h->recvCount;
             ++h->launches;
         }
         if (!h->srcAmp.empty()) finishExchange(h);  // sources overwrite halo copies of U too: the exchange of the last stage must have landed
@@ -833,6 +852,41 @@ int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) 
         }
         *nsteps = n;
         h->probeCount = 0;
+    });
+}
+
+int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights) {
+    return guarded([&] {
+        if (!h || nrecv < 0 || (nrecv > 0 && (!el || !weights))) throw DgbException(DGB_ERR_ARG, "bad receiver arguments");
+        std::vector<int32_t> loc(nrecv);
+        for (int j = 0; j < nrecv; ++j) {
+            if (el[j] < 0 || el[j] >= h->Kglobal) throw DgbException(DGB_ERR_ARG, "receiver element out of range");
+            const int l = h->partitioned ? h->plan.globalToLocal[el[j]] : el[j];
+            loc[j] = (l >= 0 && l < h->M.Kown) ? l : -1;  // receivers of other ranks' elements record 0
+        }
+        std::vector<double> w(weights, weights + (size_t)nrecv * h->Np);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->dRecvEl) { cudaFree(h->dRecvEl); h->dRecvEl = nullptr; }
+        if (h->dRecvW) { cudaFree(h->dRecvW); h->dRecvW = nullptr; }
+        if (h->dRecvRec) { cudaFree(h->dRecvRec); h->dRecvRec = nullptr; }
+        h->dRecvEl = devUpload(loc);
+        h->dRecvW = devUpload(w);
+        h->nrecv = nrecv;
+        h->recvCap = h->recvCount = 0;
+    });
+}
+
+int dgb_get_receivers(dgb_handle* h, double* out, int capacity_steps, int* nsteps) {
+    return guarded([&] {
+        if (!h || !nsteps) throw DgbException(DGB_ERR_ARG, "null argument");
+        const int n = std::min(h->recvCount, capacity_steps);
+        if (n > 0 && h->nrecv > 0) {
+            if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
+            CUDA_CHECK(cudaMemcpyAsync(out, h->dRecvRec, (size_t)n * h->nrecv * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+        *nsteps = n;
+        h->recvCount = 0;
     });
 }
 

@@ -68,6 +68,7 @@ StageKernel selectWsKernel(int dim, int order);     // warp-specialised DMMA ker
 
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);
+void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s);
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
 

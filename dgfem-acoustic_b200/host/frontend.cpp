@@ -118,6 +118,7 @@ extern "C" void dgf_default_config(dgf_config* c) {
     std::strcpy(c->saveFile, "results.msh");
     c->numThreads = 1;
     c->rho0 = 1; c->c0 = 1;
+    std::strcpy(c->receiverFile, "receivers.txt");
 }
 
 static std::vector<std::string> splitCsv(const std::string& s) {
@@ -190,6 +191,14 @@ extern "C" int dgf_parse_config(const char* path, const dgf_model* model, dgf_co
                 double* q = c->initConditions[c->nInit++];
                 q[0] = 0;
                 for (int k = 1; k <= 5; ++k) q[k] = std::stod(sep[k]);
+            } else if (it.first == "receiverFile") {
+                std::snprintf(c->receiverFile, sizeof c->receiverFile, "%s", it.second.c_str());
+            } else if (it.first.rfind("receiver", 0) == 0) {  // not a key of the reference: it skips it
+                auto sep = splitCsv(it.second);
+                if (sep.size() < 3) throw std::runtime_error("receiver needs 3 comma-separated coordinates: " + it.first);
+                if (c->nReceivers >= DGF_MAX_RECEIVERS) throw std::runtime_error("too many receivers");
+                double* r = c->receivers[c->nReceivers++];
+                for (int k = 0; k < 3; ++k) r[k] = std::stod(sep[k]);
             }
         }
         // boundary conditions by physical-group name (configParser.cpp:117-132)
@@ -521,6 +530,122 @@ extern "C" int dgf_nearest_node(const dgf_mesh* mesh, double x, double y, double
         if (r < best) { best = r; arg = (int)n; }
     }
     return arg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// receivers: point location + Lagrange interpolation weights, time-series writers
+// ---------------------------------------------------------------------------------------------
+extern "C" int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double z, double* weights, double* uvwOut, int* outside) {
+    try {
+        if (!mesh || !weights) throw std::runtime_error("dgf_locate_point: null argument");
+        const dgb_desc& d = mesh->d;
+        const int dim = d.dim, Np = d.Np;
+        const gml::RefElement& ref = gml::refElement(dim, d.order);
+        const double* u0 = &ref.uvw[0];  // parametric coordinates of local node 0
+        const double X[3] = {x, y, z};
+        int best = -1;
+        double bestViol = 1e300, bestU[3] = {0, 0, 0};
+        for (int el = 0; el < d.K; ++el) {
+            // x = x_node0 + sum_u (u_u - u0_u) J_u ,  J_u = elJacobian[el][u*3 + .] ; least squares for elements embedded in 3D
+            const double* J = &mesh->elJacobian[(size_t)el * d.nGeomEl * 9];
+            const double* x0 = &mesh->nodeCoords[(size_t)el * Np * 3];
+            double r[3] = {X[0] - x0[0], X[1] - x0[1], X[2] - x0[2]};
+            double G[3][3], b[3], du[3] = {0, 0, 0};
+            for (int a = 0; a < dim; ++a) {
+                b[a] = dot3(&J[a * 3], r);
+                for (int c = 0; c < dim; ++c) G[a][c] = dot3(&J[a * 3], &J[c * 3]);
+            }
+            if (dim == 1) du[0] = b[0] / G[0][0];
+            else if (dim == 2) {
+                const double det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
+                du[0] = (b[0] * G[1][1] - G[0][1] * b[1]) / det;
+                du[1] = (G[0][0] * b[1] - b[0] * G[1][0]) / det;
+            } else {
+                const double det = G[0][0] * (G[1][1] * G[2][2] - G[1][2] * G[2][1]) - G[0][1] * (G[1][0] * G[2][2] - G[1][2] * G[2][0]) +
+                                   G[0][2] * (G[1][0] * G[2][1] - G[1][1] * G[2][0]);
+                for (int k = 0; k < 3; ++k) {  // Cramer
+                    double A[3][3];
+                    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) A[a][c] = c == k ? b[a] : G[a][c];
+                    du[k] = (A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                             A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) / det;
+                }
+            }
+            double u[3] = {0, 0, 0};
+            for (int a = 0; a < dim; ++a) u[a] = u0[a] + du[a];
+            // barycentric coordinates: line on [-1,1], unit triangle / tetrahedron
+            double lmin;
+            if (dim == 1) lmin = std::min(0.5 * (1 - u[0]), 0.5 * (1 + u[0]));
+            else {
+                double l0 = 1;
+                lmin = 1e300;
+                for (int a = 0; a < dim; ++a) { l0 -= u[a]; lmin = std::min(lmin, u[a]); }
+                lmin = std::min(lmin, l0);
+            }
+            const double viol = lmin >= -1e-12 ? 0.0 : -lmin;
+            if (viol < bestViol) {
+                bestViol = viol; best = el;
+                std::copy(u, u + 3, bestU);
+                if (viol == 0.0) break;  // ascending scan: the lowest element id that contains the point
+            }
+        }
+        if (best < 0) throw std::runtime_error("dgf_locate_point: empty mesh");
+        ref.basis(bestU, weights);
+        if (uvwOut) std::copy(bestU, bestU + 3, uvwOut);
+        if (outside) *outside = bestViol > 0.0;
+        return best;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+extern "C" int dgf_write_receivers(const char* path, int nrecv, const double* xyz, int nsteps, double tStart, double dt, const double* rec) {
+    try {
+        if (!path || nrecv < 0 || nsteps < 0 || (nrecv > 0 && (!xyz || (nsteps > 0 && !rec)))) throw std::runtime_error("dgf_write_receivers: bad arguments");
+        std::FILE* fp = std::fopen(path, "w");
+        if (!fp) throw std::runtime_error(std::string("cannot open ") + path);
+        std::fprintf(fp, "# receivers: %d, steps: %d, columns: t then (p vx vy vz) per receiver\n", nrecv, nsteps);
+        for (int j = 0; j < nrecv; ++j) std::fprintf(fp, "# receiver %d at %.17g %.17g %.17g\n", j, xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]);
+        double t = tStart;
+        for (int k = 0; k < nsteps; ++k, t += dt) {  // the same accumulation as the loop header, solver.cpp:216
+            std::fprintf(fp, "%.17g", t);
+            for (int j = 0; j < nrecv; ++j)
+                for (int q = 0; q < 4; ++q) std::fprintf(fp, " %.17g", rec[((size_t)k * nrecv + j) * 4 + q]);
+            std::fprintf(fp, "\n");
+        }
+        std::fclose(fp);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+extern "C" int dgf_write_wav(const char* path, int nrecv, int receiver, int field, int nsteps, double dt, int rate, const double* rec) {
+    try {
+        if (!path || !rec || receiver < 0 || receiver >= nrecv || field < 0 || field > 3 || nsteps < 1 || !(dt > 0 || rate > 0))
+            throw std::runtime_error("dgf_write_wav: bad arguments");
+        const uint32_t sr = rate > 0 ? (uint32_t)rate : (uint32_t)std::llround(1.0 / dt);
+        double peak = 0;
+        for (int k = 0; k < nsteps; ++k) peak = std::max(peak, std::fabs(rec[((size_t)k * nrecv + receiver) * 4 + field]));
+        std::vector<int16_t> pcm(nsteps);
+        for (int k = 0; k < nsteps; ++k)
+            pcm[k] = peak > 0 ? (int16_t)std::lround(32767.0 * rec[((size_t)k * nrecv + receiver) * 4 + field] / peak) : (int16_t)0;
+        std::FILE* fp = std::fopen(path, "wb");
+        if (!fp) throw std::runtime_error(std::string("cannot open ") + path);
+        const uint32_t dataBytes = (uint32_t)nsteps * 2, riff = 36 + dataBytes, fmtLen = 16, byteRate = sr * 2;
+        const uint16_t pcmTag = 1, channels = 1, blockAlign = 2, bits = 16;
+        std::fwrite("RIFF", 1, 4, fp); std::fwrite(&riff, 4, 1, fp); std::fwrite("WAVEfmt ", 1, 8, fp);
+        std::fwrite(&fmtLen, 4, 1, fp); std::fwrite(&pcmTag, 2, 1, fp); std::fwrite(&channels, 2, 1, fp);
+        std::fwrite(&sr, 4, 1, fp); std::fwrite(&byteRate, 4, 1, fp); std::fwrite(&blockAlign, 2, 1, fp); std::fwrite(&bits, 2, 1, fp);
+        std::fwrite("data", 1, 4, fp); std::fwrite(&dataBytes, 4, 1, fp);
+        std::fwrite(pcm.data(), 2, pcm.size(), fp);
+        std::fclose(fp);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

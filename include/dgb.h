@@ -114,6 +114,14 @@ int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx);
  * by another rank are returned as 0. */
 int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps);
 
+/* Receivers (new capability): receiver j records the four fields interpolated at a point inside
+ * element el[j], value_q = sum_n weights[j][n] * u[q][el[j]*Np + n] with weights = the element's Lagrange basis at
+ * the point (dgf_locate_point in include/dgfront.h computes both), at the START of every step like the probes.
+ * el uses global element ids; receivers whose element another rank owns are returned as 0. */
+int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights /* [nrecv][Np] */);
+/* out[step][receiver][4]; returns the number of recorded steps in *nsteps and clears the record. */
+int dgb_get_receivers(dgb_handle* h, double* out, int capacity_steps, int* nsteps);
+
 /* ---- time marching ----------------------------------------------------------------------------------- */
 /* Advances nsteps steps starting at time t_start, accumulating t += dt in double exactly like the loop
  * header src/solver.cpp:216-217; *t_end (optional) receives the accumulated time. The state never leaves
@@ -129,7 +137,7 @@ int dgb_synchronize(dgb_handle* h);
 double dgb_last_run_ms(dgb_handle* h);        /* CUDA-event time of the last dgb_run */
 double dgb_last_stage_kernel_ms(dgb_handle* h); /* mean CUDA-event duration of the stage kernel in the last run */
 int64_t dgb_launch_count(dgb_handle* h);      /* kernels launched by this handle so far */
-int dgb_set_option(dgb_handle* h, const char* key, int value); /* "kernel": 0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow); "overlap": -1 automatic (default), 0 none, 1 same-stage, 2 next-stage; "sm_reserve": SMs left to NCCL during overlapped launches; "graph": -1 automatic / 0 / 1 CUDA graph of an RK4 step (one GPU, no sources / probes); "time_stages": 0/1 */
+int dgb_set_option(dgb_handle* h, const char* key, int value); /* "kernel": 0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow); "overlap": -1 automatic (default), 0 none, 1 same-stage, 2 next-stage; "sm_reserve": SMs left to NCCL during overlapped launches; "graph": -1 automatic / 0 / 1 CUDA graph of an RK4 step (one GPU, no sources / probes / receivers); "time_stages": 0/1 */
 const char* dgb_kernel_name(dgb_handle* h);   /* which stage kernel the handle selected */
 const char* dgb_last_error(void);
 const char* dgb_version(void);

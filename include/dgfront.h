@@ -19,6 +19,7 @@ typedef struct dgf_mesh dgf_mesh;   /* the reference's Mesh object, as plain arr
 #define DGF_MAX_SOURCES 64
 #define DGF_MAX_INIT 32
 #define DGF_MAX_PHYS 64
+#define DGF_MAX_RECEIVERS 64
 
 /* struct Config, include/configParser.h:7-41 */
 typedef struct dgf_config {
@@ -35,6 +36,12 @@ typedef struct dgf_config {
     int32_t nPhysBC;
     int32_t physBCTag[DGF_MAX_PHYS];  /* ascending physical tag (std::map order, configParser.h:23) */
     int32_t physBCType[DGF_MAX_PHYS]; /* 0 "Absorbing", 1 "Reflecting" */
+    /* Receivers — keys the reference's parser ignores (it only looks at `source*`,
+     * `initialCondtition*` and the physical-group names, configParser.cpp:65-132), so one file serves both programs:
+     *   receiver<name> = x, y, z      (std::map order of the keys)      receiverFile = path   (default receivers.txt) */
+    int32_t nReceivers;
+    double receivers[DGF_MAX_RECEIVERS][3];
+    char receiverFile[512];
 } dgf_config;
 
 const char* dgf_last_error(void);
@@ -73,6 +80,19 @@ int dgf_source_nodes(const dgf_mesh* mesh, const dgf_config* cfg, int32_t* offse
 int dgf_time_loop(const dgf_config* cfg, int32_t* snapshotSteps, int capacity, int* nSnapshots);
 /* nearest DG node to a point (probe placement helper; probes are a new capability) */
 int dgf_nearest_node(const dgf_mesh* mesh, double x, double y, double z);
+
+/* Receivers: finds the element that contains (x,y,z) — the lowest element id if the point lies on
+ * a shared face / edge / vertex; if the point is outside the mesh, the element it violates least, with *outside = 1 —
+ * and evaluates that element's Np Lagrange basis functions at the point (weights[Np]; uvw[3] optional = the
+ * parametric coordinates). Straight-sided elements (the affine inverse map). Returns the element id, -1 on error. */
+int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double z, double* weights, double* uvw, int* outside);
+/* Receiver time series as text: one line per step, `t  p vx vy vz` per receiver; a header names the points.
+ * rec is [nsteps][nrecv][4] as dgb_get_receivers returns it; t_k accumulates t += dt like the loop header. */
+int dgf_write_receivers(const char* path, int nrecv, const double* xyz /* [nrecv][3] */, int nsteps, double tStart,
+                        double dt, const double* rec);
+/* One field of one receiver as 16-bit mono PCM WAV, peak-normalised (the receiver audio of the reference's assets/);
+ * the sample rate is round(1/dt) unless rate > 0. field: 0 p, 1..3 velocity. */
+int dgf_write_wav(const char* path, int nrecv, int receiver, int field, int nsteps, double dt, int rate, const double* rec);
 
 /* Gmsh-compatible output: appends $ElementNodeData views to `path` (MSH 4.0 ASCII, after a copy of the mesh
  * on first use), the way gmsh::view::write(tag, saveFile, append=true) does at src/solver.cpp:289-291. */

@@ -145,6 +145,9 @@ struct Oracle {
 
     // ---- sources ----
     std::vector<int32_t> srcOff, srcIdx;
+    // receivers (a new capability next to the path): field values interpolated inside an element
+    std::vector<int32_t> rcvEl;
+    std::vector<double> rcvW, rcvRec;  // [nrcv][Np] Lagrange weights; record [step][nrcv][4]
     std::vector<double> srcAmp, srcFreq, srcPhase, srcDur;
 
     explicit Oracle(const dgb_desc& d, int nthreads) {
@@ -541,6 +544,12 @@ struct Oracle {
         for (int step = 0; step < nsteps; ++step, t += dt) {
             for (int j = 0; j < nprobe; ++j)
                 for (int q = 0; q < 4; ++q) probeOut[((size_t)step * nprobe + j) * 4 + q] = u[(size_t)q * N + probeIdx[j]];
+            for (size_t j = 0; j < rcvEl.size(); ++j)  // same instant as the probes / the reference's snapshots (solver.cpp:222)
+                for (int q = 0; q < 4; ++q) {
+                    double s = 0;
+                    for (int n = 0; n < Np; ++n) s += rcvW[j * Np + n] * u[(size_t)q * N + (size_t)rcvEl[j] * Np + n];
+                    rcvRec.push_back(s);
+                }
             applySources(u, t);
             if (integrator == DGB_EULER1) {
                 stageInPlace(mode, u, 1.0, scratch);
@@ -587,6 +596,24 @@ int orc_set_sources(void* h, int nsrc, const int32_t* offsets, const int32_t* no
     o->srcPhase.assign(phase, phase + nsrc);
     o->srcDur.assign(duration, duration + nsrc);
     return 0;
+}
+
+int orc_set_receivers(void* h, int nrcv, const int32_t* el, const double* weights) {
+    auto* o = static_cast<Oracle*>(h);
+    o->rcvEl.assign(el, el + nrcv);
+    o->rcvW.assign(weights, weights + (size_t)nrcv * o->Np);
+    o->rcvRec.clear();
+    return 0;
+}
+
+// out[step][receiver][4]; returns the number of recorded steps and clears the record
+int orc_get_receivers(void* h, double* out, int capacity_steps) {
+    auto* o = static_cast<Oracle*>(h);
+    const size_t per = o->rcvEl.size() * 4;
+    const int n = per ? (int)std::min<size_t>(o->rcvRec.size() / per, (size_t)capacity_steps) : 0;
+    std::copy(o->rcvRec.begin(), o->rcvRec.begin() + (size_t)n * per, out);
+    o->rcvRec.clear();
+    return n;
 }
 
 int orc_run(void* h, int mode, int integrator, double* u, double t_start, int nsteps, int nprobe, const int32_t* probeIdx,

@@ -34,6 +34,8 @@ def load_oracle():
     lib.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_double, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p]
     lib.orc_create.restype = C.c_void_p
     lib.orc_eval_rhs.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
+    lib.orc_set_receivers.argtypes = [C.c_void_p, C.c_int, c_int32_p, c_double_p]
+    lib.orc_get_receivers.argtypes = [C.c_void_p, c_double_p, C.c_int]
     lib.orc_get_operators.argtypes = [C.c_void_p, c_double_p, c_double_p]
     _oracle = lib
     return lib
@@ -52,6 +54,7 @@ class Oracle:
         if not self.h:
             raise RuntimeError("oracle: " + self.lib.orc_last_error().decode())
         self.nprobe = 0
+        self.nrcv = 0
 
     def set_sources_from_config(self):
         src = self.mesh.cfg.sources
@@ -62,6 +65,19 @@ class Oracle:
         a, f, p, d = (np.ascontiguousarray(s[:, k], dtype=np.float64) for k in (5, 6, 7, 8))
         self.lib.orc_set_sources(self.h, len(a), _as(c_int32_p, offsets), _as(c_int32_p, idx), _as(c_double_p, a),
                                  _as(c_double_p, f), _as(c_double_p, p), _as(c_double_p, d))
+
+    def set_receivers(self, el, weights):
+        """Receivers: value = sum_n weights[j][n] * u[q][el[j]*Np + n], recorded at the start of every step."""
+        el = np.ascontiguousarray(el, dtype=np.int32)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (len(el), self.mesh.Np)
+        self.nrcv = len(el)
+        self.lib.orc_set_receivers(self.h, len(el), _as(c_int32_p, el), _as(c_double_p, w))
+
+    def get_receivers(self, capacity_steps):
+        out = np.zeros((max(capacity_steps, 1), max(self.nrcv, 1), 4), dtype=np.float64)
+        n = self.lib.orc_get_receivers(self.h, _as(c_double_p, out), int(capacity_steps))
+        return out[:n, : self.nrcv]
 
     def run(self, mode, integrator, u, t_start, nsteps, probes=None):
         """Advances u in place; returns (t_end, probe record [nsteps][nprobe][4])."""
