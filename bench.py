@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--overlap", type=int, default=None, help="halo exchange overlap mode 0/1/2 (default: the engine's)")
     ap.add_argument("--sm-reserve", type=int, default=None, help="SMs left to the halo-exchange kernels during overlapped launches")
+    ap.add_argument("--exchange", type=int, default=None, help="halo exchange: 0 ncclSend/ncclRecv, 1 direct peer-to-peer stores (default: the engine's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     args = ap.parse_args()
@@ -265,7 +266,7 @@ def main():
         for _ in range(max(1, min(args.warmup, 1))):
             res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
         wall = time.perf_counter() - t0
-        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": 0, "steps": steps, "warmup": args.warmup,
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
                 "ms_per_step": res["seconds"] / args.cpu_steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -316,6 +317,9 @@ def main():
             eng.set_option("overlap", args.overlap)
         if args.sm_reserve is not None:
             eng.set_option("sm_reserve", args.sm_reserve)
+        if args.exchange is not None:
+            eng.set_option("exchange", args.exchange)
+            config["exchange"] = "p2p" if args.exchange else "nccl"
     else:
         eng = pkg.Engine(mesh)
     if args.kernel:

@@ -44,6 +44,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -66,6 +67,7 @@ NcclApi& nccl() {
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.ok = true;
     return api;
@@ -161,6 +163,19 @@ struct dgb_handle {
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int32_t* dSendElems = nullptr;
     double* hostStage = nullptr;  // pinned, [4][stride], partitioned handles only
+    // direct peer-to-peer halo exchange (dgb_set_option("exchange", 1), halo_p2p.cu): U / YA / YB and the epoch flags live in
+    // ONE allocation ("arena") that every peer maps through CUDA IPC
+    int exchangeMode = 0;            // 0: ncclSend/ncclRecv, 1: stores into the peers' halo slots + epoch flags
+    char* arena = nullptr;           // owns U, YA, YB once P2P is set up
+    double* phys[3] = {nullptr, nullptr, nullptr};  // allocation identity of the three exchanged arrays (the names U/YA swap in Euler runs)
+    struct PeerMap { void* opened = nullptr; char* base = nullptr; int64_t stride = 0; size_t arrayBytes = 0, flagOffset = 0; };
+    std::vector<PeerMap> peerMap;    // per plan.peers[i]
+    size_t arenaArrayBytes = 0, arenaFlagOffset = 0;
+    unsigned long long* dFlags = nullptr;  // [nranks] inside the arena, slot r is written by rank r
+    unsigned long long epoch = 0;
+    int32_t *dSendPeer = nullptr, *dSendSlot = nullptr;
+    int* p2pErr = nullptr;           // pinned + mapped: the wait kernel reports a timeout here
+    int p2pTimeoutMs = 20000;
 };
 
 namespace {
@@ -173,6 +188,15 @@ void freeHandle(dgb_handle* h) {
     if (h->comm) nccl().CommDestroy(h->comm);
     if (h->stepGraph) cudaGraphExecDestroy(h->stepGraph);
     if (h->hostStage) cudaFreeHost(h->hostStage);
+    for (auto& pm : h->peerMap) if (pm.opened) cudaIpcCloseMemHandle(pm.opened);
+    if (h->arena && h->comm && h->stream) {
+        // peers still map this rank's arena: every rank closes its mappings (above) before anybody frees (collective destroy)
+        char* scratch = h->arena + h->arenaFlagOffset + 128;  // the second half of the flag block is unused
+        if (nccl().AllGather(scratch + h->plan.rank, scratch, 1, ncclChar, h->comm, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
+    }
+    if (h->p2pErr) cudaFreeHost(h->p2pErr);
+    if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
+    F(h->dSendPeer); F(h->dSendSlot);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -466,7 +490,7 @@ void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     if (eEnd <= eBegin) return;
     A.eBegin = eBegin;
     A.eEnd = eEnd;
-    A.smReserve = (h->partitioned && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches only
+    A.smReserve = (h->partitioned && h->exchangeMode == 0 && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches beside NCCL kernels only
     const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
     if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
     h->active.launch(h->M, A, h->stream);
@@ -494,10 +518,150 @@ void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
     NCCL_CHECK(nccl().GroupEnd());
 }
 
+// ---- direct peer-to-peer exchange (opt-in) ---------------------------------------------------------------------------
+// Collective over the handle's communicator: every rank moves U / YA / YB into one arena, publishes its CUDA IPC handle,
+// the offset of the arena inside the underlying allocation, its array stride and, per peer, the first halo slot that
+// peer's elements occupy; then maps the arenas of its peers.
+struct P2PRecord {
+    cudaIpcMemHandle_t mem;
+    int64_t offset;      // arena - base of the allocation the IPC handle names
+    int64_t stride;      // Ktot * Np of the publishing rank
+    int64_t arrayBytes, flagOffset;
+    int32_t slot0[MAX_PEERS];  // [r] first local element slot of rank r's halo elements (-1: not a peer)
+    int32_t count[MAX_PEERS];  // [r] number of halo elements expected from rank r
+    int32_t device;
+};
+
+void setupP2P(dgb_handle* h) {
+    if (!h->partitioned) throw DgbException(DGB_ERR_UNSUPPORTED, "exchange = 1 needs a partitioned handle");
+    if (!h->peerMap.empty() || h->arena) return;
+    if (h->nranks > MAX_PEERS) throw DgbException(DGB_ERR_UNSUPPORTED, "direct exchange supports at most 16 ranks");
+    const PartitionPlan& P = h->plan;
+    const int rank = P.rank, nranks = h->nranks;
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (h->commStream) CUDA_CHECK(cudaStreamSynchronize(h->commStream));
+    // 1. arena: three state arrays (256-byte aligned) + one flag per rank
+    const size_t stateBytes = (size_t)4 * h->M.stride * sizeof(double);
+    const size_t arrBytes = (stateBytes + 255) / 256 * 256;
+    const size_t flagOff = 3 * arrBytes, total = flagOff + 256;
+    char* arena = nullptr;
+    CUDA_CHECK(cudaMalloc(&arena, total));
+    CUDA_CHECK(cudaMemset(arena, 0, total));
+    double* old[3] = {h->U, h->YA, h->YB};
+    for (int k = 0; k < 3; ++k) CUDA_CHECK(cudaMemcpy(arena + k * arrBytes, old[k], stateBytes, cudaMemcpyDeviceToDevice));
+    // 2. publish
+    std::vector<P2PRecord> rec(nranks);
+    P2PRecord& me = rec[rank];
+    std::memset(&me, 0, sizeof(me));
+    CUDA_CHECK(cudaIpcGetMemHandle(&me.mem, arena));
+    {
+        // offset of the arena inside the allocation the handle names (cudaMalloc may sub-allocate small requests)
+        typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        unsigned long long base = 0;
+        size_t sz = 0;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+            reinterpret_cast<GetRangeFn>(fn)(&base, &sz, (unsigned long long)(uintptr_t)arena) == 0 && base)
+            me.offset = (int64_t)((unsigned long long)(uintptr_t)arena - base);
+        else
+            cudaGetLastError();
+    }
+    me.stride = h->M.stride;
+    me.arrayBytes = (int64_t)arrBytes;
+    me.flagOffset = (int64_t)flagOff;
+    for (int r = 0; r < MAX_PEERS; ++r) { me.slot0[r] = -1; me.count[r] = 0; }
+    for (size_t i = 0; i < P.peers.size(); ++i) {
+        me.slot0[P.peers[i]] = P.Kown + P.recvOffset[i];
+        me.count[P.peers[i]] = P.recvOffset[i + 1] - P.recvOffset[i];
+    }
+    CUDA_CHECK(cudaGetDevice(&me.device));
+    P2PRecord* dRec = devAlloc<P2PRecord>(nranks);
+    try {
+        CUDA_CHECK(cudaMemcpy(dRec + rank, &me, sizeof(me), cudaMemcpyHostToDevice));
+        NCCL_CHECK(nccl().AllGather(dRec + rank, dRec, sizeof(P2PRecord), ncclChar, h->comm, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaMemcpy(rec.data(), dRec, sizeof(P2PRecord) * nranks, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cudaFree(dRec);
+        cudaFree(arena);
+        throw;
+    }
+    cudaFree(dRec);
+    // 3. map the peers
+    std::vector<dgb_handle::PeerMap> maps(P.peers.size());
+    std::vector<int32_t> sendPeer(P.sendElems.size()), sendSlot(P.sendElems.size());
+    try {
+        for (size_t i = 0; i < P.peers.size(); ++i) {
+            const P2PRecord& pr = rec[P.peers[i]];
+            const int nSend = P.sendOffset[i + 1] - P.sendOffset[i];
+            if (pr.count[rank] != nSend || (nSend > 0 && pr.slot0[rank] < 0)) throw DgbException(DGB_ERR_STATE, "direct exchange: send / receive plans of two ranks disagree");
+            CUDA_CHECK(cudaIpcOpenMemHandle(&maps[i].opened, pr.mem, cudaIpcMemLazyEnablePeerAccess));
+            maps[i].base = static_cast<char*>(maps[i].opened) + pr.offset;
+            maps[i].stride = pr.stride;
+            maps[i].arrayBytes = (size_t)pr.arrayBytes;
+            maps[i].flagOffset = (size_t)pr.flagOffset;
+            const int64_t expect = ((int64_t)4 * pr.stride * (int64_t)sizeof(double) + 255) / 256 * 256;
+            if (pr.arrayBytes != expect || pr.flagOffset != 3 * pr.arrayBytes) throw DgbException(DGB_ERR_STATE, "direct exchange: inconsistent arena layout");
+            for (int k = P.sendOffset[i]; k < P.sendOffset[i + 1]; ++k) { sendPeer[k] = (int32_t)i; sendSlot[k] = pr.slot0[rank] + (k - P.sendOffset[i]); }
+        }
+        h->dSendPeer = devUpload(sendPeer);
+        h->dSendSlot = devUpload(sendSlot);
+        CUDA_CHECK(cudaHostAlloc(&h->p2pErr, sizeof(int), cudaHostAllocMapped));
+        *h->p2pErr = 0;
+    } catch (...) {
+        for (auto& pm : maps) if (pm.opened) cudaIpcCloseMemHandle(pm.opened);
+        cudaFree(arena);
+        throw;
+    }
+    // 4. commit: the arena replaces the three separate arrays
+    for (int k = 0; k < 3; ++k) cudaFree(old[k]);
+    h->arena = arena;
+    h->arenaArrayBytes = arrBytes;
+    h->arenaFlagOffset = flagOff;
+    h->U = h->phys[0] = reinterpret_cast<double*>(arena);
+    h->YA = h->phys[1] = reinterpret_cast<double*>(arena + arrBytes);
+    h->YB = h->phys[2] = reinterpret_cast<double*>(arena + 2 * arrBytes);
+    h->dFlags = reinterpret_cast<unsigned long long*>(arena + flagOff);
+    h->peerMap.swap(maps);
+    h->epoch = 0;
+}
+
+// push the owned cut-adjacent elements of `produced` into the peers' halo slots and raise this rank's flag there
+void pushHalo(dgb_handle* h, double* produced) {
+    const PartitionPlan& P = h->plan;
+    int which = -1;
+    for (int k = 0; k < 3; ++k) if (produced == h->phys[k]) which = k;
+    if (which < 0) throw DgbException(DGB_ERR_STATE, "direct exchange: produced array is not one of the exchanged arrays");
+    PeerTargets T{};
+    PeerFlags F{};
+    F.n = (int)P.peers.size();
+    for (size_t i = 0; i < P.peers.size(); ++i) {
+        const dgb_handle::PeerMap& pm = h->peerMap[i];
+        T.arr[i] = reinterpret_cast<double*>(pm.base + (size_t)which * pm.arrayBytes);
+        T.stride[i] = pm.stride;
+        F.flag[i] = reinterpret_cast<unsigned long long*>(pm.base + pm.flagOffset) + P.rank;
+    }
+    ++h->epoch;
+    launchPushHalo(produced, h->M.stride, h->Np, h->dSendElems, h->dSendPeer, h->dSendSlot, (int)P.sendElems.size(), T, h->stream);
+    launchSignalPeers(F, h->epoch, h->stream);
+    h->launches += 2;
+}
+
+void waitHalo(dgb_handle* h) {
+    const PartitionPlan& P = h->plan;
+    PeerWait W{};
+    W.n = (int)P.peers.size();
+    for (size_t i = 0; i < P.peers.size(); ++i) W.rank[i] = P.peers[i];
+    launchWaitPeers(h->dFlags, W, h->epoch, (unsigned long long)h->p2pTimeoutMs * 1000000ull, h->p2pErr, h->stream);
+    ++h->launches;
+}
+
 // Effective overlap mode. Measured on B200 (config 5, profiles/r01w_scale_*.json): the persistent DMMA kernels pay more for a
 // second, small launch per stage (prologue, pipeline fill / drain, static tile lists) than the ~0.09 ms exchange costs, at 2, 4
 // and 8 GPUs alike, so they run one launch per stage and exchange afterwards; the light-weight generic kernel overlaps.
 int overlapMode(const dgb_handle* h) {
+    if (h->exchangeMode == 1) return h->overlap >= 1 ? 1 : h->overlap == 0 ? 0 : (h->active.launch == h->generic.launch ? 1 : 0);  // no deferred order
     if (h->overlap >= 0) return h->overlap;
     return h->active.launch == h->generic.launch ? 1 : 0;
 }
@@ -517,6 +681,20 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
     }
     const int nSendEl = (int)P.sendElems.size();
     const int overlap = overlapMode(h);
+    if (h->exchangeMode == 1) {
+        // direct stores into the peers' halo slots: the transfer needs no second stream, it drains over NVLink while the
+        // interior elements run (overlap 1) or is simply waited for (overlap 0)
+        if (overlap == 1) {
+            launchStage(h, A, P.Kinterior, P.Kown, false);
+            pushHalo(h, produced);
+            launchStage(h, A, 0, P.Kinterior, true);
+        } else {
+            launchStage(h, A, 0, h->M.Kown, true);
+            pushHalo(h, produced);
+        }
+        waitHalo(h);
+        return;
+    }
     if (overlap == 2) {
         launchStage(h, A, 0, P.Kinterior, true);
         if (h->recvPending) {
@@ -656,6 +834,11 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
     CUDA_CHECK(cudaEventRecord(h->evStop, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     CUDA_CHECK(cudaGetLastError());
+    if (h->p2pErr && *h->p2pErr) {
+        const int who = *h->p2pErr - 1;
+        *h->p2pErr = 0;
+        throw DgbException(DGB_ERR_STATE, "direct exchange: timed out waiting for the halo of rank " + std::to_string(who));
+    }
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, h->evStart, h->evStop));
     h->lastRunMs = ms;
@@ -947,6 +1130,12 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             if (value < -1 || value > 2) throw DgbException(DGB_ERR_ARG, "overlap must be -1 (automatic), 0, 1 or 2");
             h->overlap = value;
         }
+        else if (k == "exchange") {  // collective: every rank of the communicator must make the same call
+            if (value != 0 && value != 1) throw DgbException(DGB_ERR_ARG, "exchange must be 0 (NCCL send/recv) or 1 (direct peer-to-peer stores)");
+            finishExchange(h);
+            if (value == 1) setupP2P(h);
+            h->exchangeMode = value;
+        } else if (k == "p2p_timeout_ms") h->p2pTimeoutMs = std::max(1, value);
         else if (k == "sm_reserve") h->smReserve = std::max(0, value);
         else if (k == "graph") h->useGraph = value < 0 ? -1 : (value ? 1 : 0);
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -71,5 +72,16 @@ void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int
 void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s);
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
+
+// direct peer-to-peer halo exchange (halo_p2p.cu); tables are passed by value as kernel arguments
+constexpr int MAX_PEERS = 16;
+struct PeerTargets { double* arr[MAX_PEERS]; long long stride[MAX_PEERS]; };   // the peers' copy of the produced array, [4][stride]
+struct PeerFlags { unsigned long long* flag[MAX_PEERS]; int n; };              // THIS rank's slot in each peer's flag array
+struct PeerWait { int rank[MAX_PEERS]; int n; };                               // ranks whose flags this rank waits for
+void launchPushHalo(const double* y, int64_t stride, int Np, const int32_t* sendElems, const int32_t* sendPeer, const int32_t* sendSlot,
+                    int nSend, const PeerTargets& T, cudaStream_t s);
+void launchSignalPeers(const PeerFlags& F, unsigned long long epoch, cudaStream_t s);
+void launchWaitPeers(const unsigned long long* flags, const PeerWait& W, unsigned long long epoch, unsigned long long timeoutNs, int* err,
+                     cudaStream_t s);
 
 }  // namespace dgb

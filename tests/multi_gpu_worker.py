@@ -21,6 +21,7 @@ def main():
 
     out_dir, cells, order, steps, overlap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     flow = int(sys.argv[6]) if len(sys.argv) > 6 else 1  # 0: zero mean flow (warp-specialised kernel at orders 3, 4)
+    exchange = int(sys.argv[7]) if len(sys.argv) > 7 else 0  # 1: direct peer-to-peer stores instead of ncclSend/ncclRecv
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -42,22 +43,28 @@ def main():
     probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5), mesh.nearest_node(-7, 3, -2)], dtype=np.int32)
     u0 = mesh.initial_condition()
     eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes(), options={"overlap": overlap})
+    if exchange:
+        eng.set_option("p2p_timeout_ms", 5000)
+        eng.set_option("exchange", exchange)  # collective
     eng.set_sources_from_config()
     eng.set_probes(probes)
     eng.set_state(u0)
-    eng.run(pkg.RUNGE_KUTTA, 0.0, steps)
+    t_half = eng.run(pkg.RUNGE_KUTTA, 0.0, steps // 2)
+    eng.run(pkg.RUNGE_KUTTA, t_half, steps - steps // 2)
     got = np.full((4, mesh.N), np.nan)
     eng.get_state(got)
     rec = eng.get_probes(steps)
     owned = np.repeat(part == rank, mesh.Np)
     np.savez(Path(out_dir) / f"rank{rank}.npz", u=got, owned=owned, probes=rec, launches=eng.launch_count)
+    dist.barrier()
     eng.close()
     if rank == 0:
         single = pkg.Engine(mesh)
         single.set_sources_from_config()
         single.set_probes(probes)
         single.set_state(u0)
-        single.run(pkg.RUNGE_KUTTA, 0.0, steps)
+        t_half = single.run(pkg.RUNGE_KUTTA, 0.0, steps // 2)
+        single.run(pkg.RUNGE_KUTTA, t_half, steps - steps // 2)
         np.savez(Path(out_dir) / "single.npz", u=single.get_state(), probes=single.get_probes(steps))
         single.close()
     dist.barrier()
