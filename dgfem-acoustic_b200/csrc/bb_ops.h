@@ -1,0 +1,225 @@
+// Bernstein-Bezier form of the element operators on straight-sided tetrahedra ("sparse-operator variant").
+//
+// The nodal operators Dw^u (Np x Np dense) and LIFT (Np x Nf*Nfp dense) of the reference's scheme become sparse when the
+// polynomial is carried by its Bernstein coefficients c_a, u = sum_|a|=N c_a B_a(lambda), B_a = N!/a! lambda^a, instead of
+// its values at the equispaced nodes (u_nodal = V c, V_na = B_a(x_n), cond(V) = 15 at N = 4):
+//   * derivative along a direction with barycentric weights w_j = d(lambda_j)/ds:
+//         t_b = sum_j w_j c_{b+e_j}   (|b| = N-1, 4 terms),    (du/ds)_g = sum_k g_k t_{g-e_k}   (|g| = N, <= 4 terms)
+//   * the numerical flux is linear with face-constant coefficients, so it acts on the coefficients directly, and the face
+//     trace of u is carried by the coefficients with a_J = 0 (J = the vertex opposite the face), through the same
+//     neighbour node maps as the nodal scheme (coefficient a <-> node a/N);
+//   * lift of a face vector x (|b| = N, 2D): with the unnormalised 2D degree elevation (E_M x)_g = sum_k g_k x_{g-e_k},
+//         layer 0 (a_J = 0):  y   = E_N^T E_N x
+//         layer l (a_J = l):  z_l = -1/(l+1) * E_{N-l}^T z_{l-1},   z_0 = y
+//     (Chan & Warburton's factorisation; the constants were fitted against Mref^-1 E_lf Mf of this code's reference
+//     element and hold to 1e-13 for N = 2..5, tests/test_bb_ops.py).
+// The strong form  rhs = -div F + LIFT(Fscale * (n.F(u-) - flux*))  equals the weak form the reference integrates
+// (exact quadrature on affine elements): tests compare against the oracle to 1e-12.
+//
+// Everything here is index arithmetic that unrolls completely: arrays live in registers, coefficients are small
+// integers. __host__ __device__ so that the CPU tests run the very same code the kernel runs (oracle/bb_check.cpp).
+#pragma once
+
+#if defined(__CUDACC__)
+#define BB_HD __host__ __device__ __forceinline__
+#define BB_UNROLL _Pragma("unroll")
+#else
+#define BB_HD inline
+#define BB_UNROLL
+#endif
+
+#include <stdint.h>
+
+namespace dgb {
+namespace bb {
+
+BB_HD constexpr int tri(int m) { return (m + 1) * (m + 2) / 2; }            // 2D indices of degree m
+BB_HD constexpr int tet(int m) { return (m + 1) * (m + 2) * (m + 3) / 6; }  // 3D indices of degree m
+
+// canonical order of the 3D indices a = (a0,a1,a2,a3), |a| = m: lexicographic in (a1, a2, a3), a0 = m - a1 - a2 - a3
+BB_HD constexpr int vidx(int m, int a1, int a2, int a3) {
+    // indices with a smaller a1: sum_{i<a1} tri(m-i) = tet(m) - tet(m-a1); with this a1 and a smaller a2: sum_{j<a2} (m-a1-j+1)
+    return tet(m) - tet(m - a1) + a2 * (m - a1 + 1) - a2 * (a2 - 1) / 2 + a3;
+}
+// canonical order of the 2D indices b = (b0,b1,b2), |b| = m: lexicographic in (b1, b2)
+BB_HD constexpr int fidx(int m, int b1, int b2) { return b1 * (m + 1) - b1 * (b1 - 1) / 2 + b2; }
+
+// volume index of the coefficient in layer l of face J (a_J = l) whose other three entries, in increasing vertex order,
+// are (b0, b1, b2), b0 = N - l - b1 - b2
+template <int N, int J>
+BB_HD constexpr int layerIdx(int l, int b1, int b2) {
+    const int b0 = N - l - b1 - b2;
+    // vertices other than J in increasing order: J=0 -> (1,2,3), J=1 -> (0,2,3), J=2 -> (0,1,3), J=3 -> (0,1,2)
+    const int a1 = J == 0 ? b0 : J == 1 ? l : b1;
+    const int a2 = J == 0 ? b1 : J == 1 ? b1 : J == 2 ? l : b2;
+    const int a3 = J == 0 ? b2 : J == 1 ? b2 : J == 2 ? b2 : l;
+    return vidx(N, a1, a2, a3);
+}
+
+// t_b (+)= sum_j w_j c_{b+e_j}  for |b| = N-1: the degree N-1 coefficients of the derivative of u along the direction whose
+// barycentric rates are w (up to the factor N that the elevation back to degree N cancels)
+template <int N, bool ACCUMULATE>
+BB_HD void dirDeriv(const double (&c)[tet(N)], const double (&w)[4], double (&t)[tet(N - 1)]) {
+    BB_UNROLL
+    for (int b1 = 0; b1 <= N - 1; ++b1) {
+        BB_UNROLL
+        for (int b2 = 0; b2 <= N - 1 - b1; ++b2) {
+            BB_UNROLL
+            for (int b3 = 0; b3 <= N - 1 - b1 - b2; ++b3) {
+                double s = w[0] * c[vidx(N, b1, b2, b3)];
+                s = s + w[1] * c[vidx(N, b1 + 1, b2, b3)];
+                s = s + w[2] * c[vidx(N, b1, b2 + 1, b3)];
+                s = s + w[3] * c[vidx(N, b1, b2, b3 + 1)];
+                const int i = vidx(N - 1, b1, b2, b3);
+                t[i] = ACCUMULATE ? t[i] + s : s;
+            }
+        }
+    }
+}
+
+// out_g += scale * sum_k g_k t_{g-e_k}  for |g| = N  (degree elevation N-1 -> N, unnormalised)
+template <int N>
+BB_HD void elevateAdd(const double (&t)[tet(N - 1)], double scale, double (&out)[tet(N)]) {
+    BB_UNROLL
+    for (int a1 = 0; a1 <= N; ++a1) {
+        BB_UNROLL
+        for (int a2 = 0; a2 <= N - a1; ++a2) {
+            BB_UNROLL
+            for (int a3 = 0; a3 <= N - a1 - a2; ++a3) {
+                const int a0 = N - a1 - a2 - a3;
+                double s = 0.0;
+                if (a0 > 0) s = s + a0 * t[vidx(N - 1, a1, a2, a3)];
+                if (a1 > 0) s = s + a1 * t[vidx(N - 1, a1 - 1, a2, a3)];
+                if (a2 > 0) s = s + a2 * t[vidx(N - 1, a1, a2 - 1, a3)];
+                if (a3 > 0) s = s + a3 * t[vidx(N - 1, a1, a2, a3 - 1)];
+                const int i = vidx(N, a1, a2, a3);
+                out[i] = out[i] + scale * s;
+            }
+        }
+    }
+}
+
+// (E_M^T w)_b = sum_k (b_k + 1) w_{b+e_k} : degree M+1 -> M on a triangle, scaled
+template <int M>
+BB_HD void faceLower(const double (&w)[tri(M + 1)], double scale, double (&z)[tri(M)]) {
+    BB_UNROLL
+    for (int b1 = 0; b1 <= M; ++b1) {
+        BB_UNROLL
+        for (int b2 = 0; b2 <= M - b1; ++b2) {
+            const int b0 = M - b1 - b2;
+            const double s = (b0 + 1) * w[fidx(M + 1, b1, b2)] + (b1 + 1) * w[fidx(M + 1, b1 + 1, b2)] + (b2 + 1) * w[fidx(M + 1, b1, b2 + 1)];
+            z[fidx(M, b1, b2)] = scale * s;
+        }
+    }
+}
+
+// (E_M x)_g = sum_k g_k x_{g-e_k} : degree M -> M+1 on a triangle
+template <int M>
+BB_HD void faceRaise(const double (&x)[tri(M)], double (&w)[tri(M + 1)]) {
+    BB_UNROLL
+    for (int g1 = 0; g1 <= M + 1; ++g1) {
+        BB_UNROLL
+        for (int g2 = 0; g2 <= M + 1 - g1; ++g2) {
+            const int g0 = M + 1 - g1 - g2;
+            double s = 0.0;
+            if (g0 > 0) s = s + g0 * x[fidx(M, g1, g2)];
+            if (g1 > 0) s = s + g1 * x[fidx(M, g1 - 1, g2)];
+            if (g2 > 0) s = s + g2 * x[fidx(M, g1, g2 - 1)];
+            w[fidx(M + 1, g1, g2)] = s;
+        }
+    }
+}
+
+// layers l = L .. N of face J: out[layer l] += z_l,  z_{l+1} = -1/(l+2) E_{N-l-1}^T z_l
+template <int N, int J, int L>
+struct LiftLayers {
+    static BB_HD void run(const double (&z)[tri(N - L)], double (&out)[tet(N)]) {
+        BB_UNROLL
+        for (int b1 = 0; b1 <= N - L; ++b1) {
+            BB_UNROLL
+            for (int b2 = 0; b2 <= N - L - b1; ++b2) {
+                const int i = layerIdx<N, J>(L, b1, b2);
+                out[i] = out[i] + z[fidx(N - L, b1, b2)];
+            }
+        }
+        if constexpr (L < N) {
+            double zn[tri(N - L - 1)];
+            faceLower<N - L - 1>(z, -1.0 / (L + 2), zn);
+            LiftLayers<N, J, L + 1>::run(zn, out);
+        }
+    }
+};
+
+// out += LIFT_J x : x = Fscale * (n.F(u-) - flux*) as the Bernstein coefficients of the face polynomial, canonical 2D order
+template <int N, int J>
+BB_HD void liftFace(const double (&x)[tri(N)], double (&out)[tet(N)]) {
+    double w[tri(N + 1)], y[tri(N)];
+    faceRaise<N>(x, w);
+    faceLower<N>(w, 1.0, y);
+    LiftLayers<N, J, 0>::run(y, out);
+}
+
+constexpr int MAX_ORDER = 6, MAX_NP = tet(MAX_ORDER), MAX_NFP = tri(MAX_ORDER);
+
+// Permutations between the mesh's element-local numbering and the canonical orders above (built by bb_setup.h, passed
+// to the kernels by value)
+struct Tables {
+    uint8_t permC2G[MAX_NP];      // canonical volume index -> node of the mesh's element-local numbering
+    uint8_t faceLf[4];            // canonical face J (opposite vertex J) -> local face of the mesh
+    uint8_t facePos[4][MAX_NFP];  // canonical (J, 2D index) -> position m in the mesh's face-node list of that local face
+};
+
+template <int N, int J>
+BB_HD void liftFaceFrom(const double* dphi, const Tables& T, double (&out)[tet(N)]) {
+    double x[tri(N)];
+    const int base = T.faceLf[J] * tri(N);
+    BB_UNROLL
+    for (int b = 0; b < tri(N); ++b) x[b] = dphi[base + T.facePos[J][b]];
+    liftFace<N, J>(x, out);
+}
+
+// Right-hand side of ONE field of ONE element as Bernstein coefficients in canonical order:
+//   out = -(v0.grad q + coupling) + sum_J LIFT_J dphi_J
+//   q = 0 (p):   coupling = rho0 c0^2 div v          q = 1..3 (v_x): coupling = (1/rho0) dp/dx_x
+// cols[f] points at the element's coefficients of field f (mesh node order), dphi at this field's face inputs
+// Fscale * (n.F(u-) - flux*) in the mesh's (local face, face node) order, gl[j][x] = d lambda_j / d x.
+template <int N>
+BB_HD void fieldRhs(int q, const double* const (&cols)[4], const double* dphi, const Tables& T, const double (&gl)[4][3],
+                    const double (&v0)[3], bool flow, double rc2, double invRho, double (&out)[tet(N)]) {
+    constexpr int NP = tet(N), ND = tet(N - 1);
+    double t[ND];
+    BB_UNROLL
+    for (int i = 0; i < ND; ++i) t[i] = 0.0;
+    const int nCoupling = q == 0 ? 3 : 1;
+    const int nPass = nCoupling + (flow ? 1 : 0);
+    for (int pass = 0; pass < nPass; ++pass) {  // run-time trip count: one copy of the body
+        int field;
+        double w[4];
+        if (pass < nCoupling) {
+            field = q == 0 ? 1 + pass : 0;
+            const int x = q == 0 ? pass : q - 1;
+            const double s = q == 0 ? rc2 : invRho;
+            BB_UNROLL
+            for (int j = 0; j < 4; ++j) w[j] = s * gl[j][x];
+        } else {
+            field = q;
+            BB_UNROLL
+            for (int j = 0; j < 4; ++j) w[j] = v0[0] * gl[j][0] + v0[1] * gl[j][1] + v0[2] * gl[j][2];
+        }
+        const double* col = cols[field];
+        double cc[NP];
+        BB_UNROLL
+        for (int i = 0; i < NP; ++i) cc[i] = col[T.permC2G[i]];
+        dirDeriv<N, true>(cc, w, t);
+    }
+    BB_UNROLL
+    for (int i = 0; i < NP; ++i) out[i] = 0.0;
+    elevateAdd<N>(t, -1.0, out);
+    liftFaceFrom<N, 0>(dphi, T, out);
+    liftFaceFrom<N, 1>(dphi, T, out);
+    liftFaceFrom<N, 2>(dphi, T, out);
+    liftFaceFrom<N, 3>(dphi, T, out);
+}
+
+}  // namespace bb
+}  // namespace dgb

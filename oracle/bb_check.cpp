@@ -1,0 +1,147 @@
+// CPU checker of the Bernstein-Bezier path — TEST INFRASTRUCTURE ONLY (like everything under oracle/).
+//
+// Runs the product's own operator code (dgfem-acoustic_b200/csrc/bb_ops.h, bb_setup.h: the very templates the CUDA
+// kernel stage_bb.cu instantiates) on the host, element by element, around a plain restatement of the face-flux
+// formulas of the reference (Mesh.cpp:519-527 interior, :616-648 reflecting, :391-418 + :652-667 absorbing, the same
+// expressions as oracle.cpp's operator mode), so that tests can compare  V * rhs_Bernstein(V^-1 u)  with the oracle's
+// L(u) without a GPU. Nothing in the product links or loads this file.
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../dgfem-acoustic_b200/csrc/bb_setup.h"
+
+using namespace dgb::bb;
+
+namespace {
+thread_local std::string g_err;
+
+template <int N>
+void evalRhs(const dgb_desc& d, const Setup& S, const double* u, double* rhs) {
+    constexpr int NP = tet(N), NFP = tri(N);
+    const int K = d.K;
+    const size_t Ntot = (size_t)K * NP;
+    const double rc2 = d.rho0 * d.c0 * d.c0, invRho = 1.0 / d.rho0;
+    const bool flow = d.v0[0] != 0.0 || d.v0[1] != 0.0 || d.v0[2] != 0.0;
+    // nodal -> Bernstein, mesh node order
+    std::vector<double> c(4 * Ntot), out(4 * Ntot);
+    for (int q = 0; q < 4; ++q)
+        for (int el = 0; el < K; ++el)
+            for (int m = 0; m < NP; ++m) {
+                double s = 0;
+                for (int n = 0; n < NP; ++n) s += S.Vinv[(size_t)m * NP + n] * u[q * Ntot + (size_t)el * NP + n];
+                c[q * Ntot + (size_t)el * NP + m] = s;
+            }
+    const int gE = d.nGeomEl, gF = d.nGeomF;
+    for (int el = 0; el < K; ++el) {
+        // d lambda_j / d x from the element Jacobian (index u*3+x = dx_x/du_u): rows of its inverse, lambda_0 = 1 - sum
+        const double* Jm = &d.elJacobian[(size_t)el * gE * 9];
+        double A[3][3], B[3][3];
+        for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) A[r][cc] = Jm[r * 3 + cc];
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc) {
+                const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3, c1 = (r + 1) % 3, c2 = (r + 2) % 3;
+                B[r][cc] = (A[r1][c1] * A[r2][c2] - A[r1][c2] * A[r2][c1]) / det;  // B[x][u] = du_u/dx_x
+            }
+        double gl[4][3];
+        for (int x = 0; x < 3; ++x) {
+            gl[0][x] = -(B[x][0] + B[x][1] + B[x][2]);
+            for (int j = 1; j < 4; ++j) gl[j][x] = B[x][j - 1];
+        }
+        // face inputs Fscale * (n.F(u-) - flux*) per field, mesh (local face, face node) order
+        double dphi[4][4 * NFP];
+        for (int lf = 0; lf < 4; ++lf) {
+            const int f = d.elFId[(size_t)el * 4 + lf];
+            const int side = d.fNbrElId[2 * (size_t)f] == el ? 0 : 1;
+            const double o = d.elFOrientation[(size_t)el * 4 + lf];
+            double n[3];
+            for (int x = 0; x < 3; ++x) n[x] = o * d.fNormal[(size_t)f * gF * 3 + x];  // outward
+            const double Fs = d.fJacobianDet[(size_t)f * gF] / d.elJacobianDet[(size_t)el * gE];
+            const double v0n = d.v0[0] * n[0] + d.v0[1] * n[1] + d.v0[2] * n[2];
+            int pos[MAX_NP];
+            for (int m = 0; m < NFP; ++m) pos[S.faceNodes[(size_t)lf * NFP + m]] = m;
+            for (int k = 0; k < NFP; ++k) {
+                const int own = d.fNToElNId[((size_t)f * NFP + k) * 2 + side];
+                const int m = pos[own];
+                double qm[4], fl[4], tr[4];
+                for (int q = 0; q < 4; ++q) qm[q] = c[q * Ntot + (size_t)el * NP + own];
+                const double vn = n[0] * qm[1] + n[1] * qm[2] + n[2] * qm[3];
+                tr[0] = v0n * qm[0] + rc2 * vn;
+                for (int x = 0; x < 3; ++x) tr[1 + x] = v0n * qm[1 + x] + n[x] * qm[0] * invRho;
+                if (d.fIsBoundary[f]) {
+                    if (d.fBC[f] == 1) {
+                        double v[3];
+                        for (int x = 0; x < 3; ++x) v[x] = qm[1 + x] - vn * n[x];
+                        fl[0] = v0n * qm[0] + rc2 * (n[0] * v[0] + n[1] * v[1] + n[2] * v[2]);
+                        for (int x = 0; x < 3; ++x) fl[1 + x] = v0n * v[x] + n[x] * qm[0] * invRho;
+                    } else {
+                        fl[0] = 0.25 * d.c0 * qm[0] + 0.25 * d.c0 * d.c0 * d.rho0 * vn;
+                        for (int x = 0; x < 3; ++x) fl[1 + x] = 0.25 * n[x] * invRho * qm[0] + 0.25 * d.c0 * n[x] * vn;
+                    }
+                } else {
+                    const int nb = d.fNbrElId[2 * (size_t)f + (1 - side)];
+                    const int nbn = d.fNToElNId[((size_t)f * NFP + k) * 2 + (1 - side)];
+                    double qp[4];
+                    for (int q = 0; q < 4; ++q) qp[q] = c[q * Ntot + (size_t)nb * NP + nbn];
+                    const double tau = d.fc * o * (side == 0 ? 1.0 : -1.0);
+                    const double ps = qm[0] + qp[0];
+                    const double vns = n[0] * (qm[1] + qp[1]) + n[1] * (qm[2] + qp[2]) + n[2] * (qm[3] + qp[3]);
+                    fl[0] = 0.5 * (v0n * ps + rc2 * vns) + 0.5 * tau * d.c0 * (qm[0] - qp[0]);
+                    for (int x = 0; x < 3; ++x)
+                        fl[1 + x] = 0.5 * (v0n * (qm[1 + x] + qp[1 + x]) + n[x] * ps * invRho) + 0.5 * tau * d.c0 * (qm[1 + x] - qp[1 + x]);
+                }
+                for (int q = 0; q < 4; ++q) dphi[q][lf * NFP + m] = Fs * (tr[q] - fl[q]);
+            }
+        }
+        const double* cols[4] = {&c[(size_t)el * NP], &c[Ntot + (size_t)el * NP], &c[2 * Ntot + (size_t)el * NP], &c[3 * Ntot + (size_t)el * NP]};
+        const double* const(&colsRef)[4] = cols;
+        const double v0[3] = {d.v0[0], d.v0[1], d.v0[2]};
+        for (int q = 0; q < 4; ++q) {
+            double r[NP];
+            fieldRhs<N>(q, colsRef, dphi[q], S.T, gl, v0, flow, rc2, invRho, r);
+            for (int i = 0; i < NP; ++i) out[q * Ntot + (size_t)el * NP + S.T.permC2G[i]] = r[i];
+        }
+    }
+    // Bernstein -> nodal
+    for (int q = 0; q < 4; ++q)
+        for (int el = 0; el < K; ++el)
+            for (int n = 0; n < NP; ++n) {
+                double s = 0;
+                for (int m = 0; m < NP; ++m) s += S.V[(size_t)n * NP + m] * out[q * Ntot + (size_t)el * NP + m];
+                rhs[q * Ntot + (size_t)el * NP + n] = s;
+            }
+}
+}  // namespace
+
+extern "C" {
+
+const char* bbc_last_error(void) { return g_err.c_str(); }
+
+// rhs = L(u) through the Bernstein path, nodal in / nodal out; *liftDev (optional) = deviation of the closed-form lift
+// from the dense nodal one; alphaOut (optional, [Np][4]) = the recovered Bernstein index of every node.
+int bbc_eval_rhs(const dgb_desc* d, const double* u, double* rhs, double* liftDev, int32_t* alphaOut) {
+    try {
+        const Setup S = buildSetup(d);
+        if (alphaOut) for (size_t i = 0; i < S.alpha.size(); ++i) alphaOut[i] = S.alpha[i];
+        double dev = 0;
+        switch (d->order) {
+            case 1: dev = liftDeviation<1>(S); evalRhs<1>(*d, S, u, rhs); break;
+            case 2: dev = liftDeviation<2>(S); evalRhs<2>(*d, S, u, rhs); break;
+            case 3: dev = liftDeviation<3>(S); evalRhs<3>(*d, S, u, rhs); break;
+            case 4: dev = liftDeviation<4>(S); evalRhs<4>(*d, S, u, rhs); break;
+            case 5: dev = liftDeviation<5>(S); evalRhs<5>(*d, S, u, rhs); break;
+            case 6: dev = liftDeviation<6>(S); evalRhs<6>(*d, S, u, rhs); break;
+            default: throw std::runtime_error("order out of range");
+        }
+        if (liftDev) *liftDev = dev;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}
