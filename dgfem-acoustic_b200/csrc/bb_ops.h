@@ -181,10 +181,11 @@ BB_HD void liftFaceFrom(const double* dphi, const Tables& T, double (&out)[tet(N
 // Right-hand side of ONE field of ONE element as Bernstein coefficients in canonical order:
 //   out = -(v0.grad q + coupling) + sum_J LIFT_J dphi_J
 //   q = 0 (p):   coupling = rho0 c0^2 div v          q = 1..3 (v_x): coupling = (1/rho0) dp/dx_x
-// cols[f] points at the element's coefficients of field f (mesh node order), dphi at this field's face inputs
+// col0 + f*colStride points at the element's coefficients of field f (mesh node order), dphi at this field's face inputs
 // Fscale * (n.F(u-) - flux*) in the mesh's (local face, face node) order, gl[j][x] = d lambda_j / d x.
+// (No array is indexed with a run-time value: everything stays in registers.)
 template <int N>
-BB_HD void fieldRhs(int q, const double* const (&cols)[4], const double* dphi, const Tables& T, const double (&gl)[4][3],
+BB_HD void fieldRhs(int q, const double* col0, int colStride, const double* dphi, const Tables& T, const double (&gl)[4][3],
                     const double (&v0)[3], bool flow, double rc2, double invRho, double (&out)[tet(N)]) {
     constexpr int NP = tet(N), ND = tet(N - 1);
     double t[ND];
@@ -200,13 +201,13 @@ BB_HD void fieldRhs(int q, const double* const (&cols)[4], const double* dphi, c
             const int x = q == 0 ? pass : q - 1;
             const double s = q == 0 ? rc2 : invRho;
             BB_UNROLL
-            for (int j = 0; j < 4; ++j) w[j] = s * gl[j][x];
+            for (int j = 0; j < 4; ++j) w[j] = s * (x == 0 ? gl[j][0] : x == 1 ? gl[j][1] : gl[j][2]);
         } else {
             field = q;
             BB_UNROLL
             for (int j = 0; j < 4; ++j) w[j] = v0[0] * gl[j][0] + v0[1] * gl[j][1] + v0[2] * gl[j][2];
         }
-        const double* col = cols[field];
+        const double* col = col0 + field * colStride;
         double cc[NP];
         BB_UNROLL
         for (int i = 0; i < NP; ++i) cc[i] = col[T.permC2G[i]];

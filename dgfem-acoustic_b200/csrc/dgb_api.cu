@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "bb_setup.h"
 #include "dgb_internal.h"
 #include "partition.h"
 #include "tile_cfg.h"
@@ -130,7 +131,11 @@ struct dgb_handle {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
     std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
     int stageEvUsed = 0;
-    StageKernel generic, tiled, ws, active;
+    StageKernel generic, tiled, ws, bbKernel, active;
+    // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
+    bool bbMode = false;
+    std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
+    double *dV = nullptr, *dVinv = nullptr;
     StageKernel autoKernel() const { return ws.launch ? ws : tiled.launch ? tiled : generic; }
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
@@ -196,7 +201,7 @@ void freeHandle(dgb_handle* h) {
     }
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
-    F(h->dSendPeer); F(h->dSendSlot);
+    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -463,6 +468,33 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         if (!h->generic.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no stage kernel for this dim/order");
         if (M.v0[0] == 0.0 && M.v0[1] == 0.0 && M.v0[2] == 0.0) h->ws = selectWsKernel(dim, d->order);
         h->active = h->autoKernel();
+        // Bernstein-Bezier path (opt-in): conversion matrices, permutation tables, self-check of the closed-form lift
+        h->bbKernel = selectBBKernel(dim, d->order);
+        if (!h->bbKernel.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra, orders 2..5)";
+        else {
+            try {
+                const bb::Setup S = bb::buildSetup(d);
+                double dev = 1.0;
+                switch (d->order) {
+                    case 2: dev = bb::liftDeviation<2>(S); break;
+                    case 3: dev = bb::liftDeviation<3>(S); break;
+                    case 4: dev = bb::liftDeviation<4>(S); break;
+                    case 5: dev = bb::liftDeviation<5>(S); break;
+                    default: break;
+                }
+                if (!(dev < 1e-11)) throw std::runtime_error("closed-form lift deviates from the dense one by " + std::to_string(dev));
+                for (int lf = 0; lf < Nf; ++lf)
+                    for (int m = 0; m < Nfp; ++m)
+                        if (S.faceNodes[(size_t)lf * Nfp + m] != H.faceNodes[(size_t)lf * Nfp + m]) throw std::runtime_error("face-node tables disagree");
+                setBBTables(d->order, S.T);
+                CUDA_CHECK(cudaGetLastError());
+                h->dV = devUpload(S.V);
+                h->dVinv = devUpload(S.Vinv);
+            } catch (const std::exception& e) {
+                h->bbWhyNot = e.what();
+                h->bbKernel = StageKernel{};
+            }
+        }
 
         if (h->partitioned) {
             CUDA_CHECK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
@@ -888,6 +920,7 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
     const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
     if (!h->partitioned) {
         CUDA_CHECK(cudaMemcpyAsync(dst, u, (size_t)4 * Ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, h->M.Ktot, h->dVinv, h->stream); ++h->launches; }  // nodal -> Bernstein
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         return;
     }
@@ -902,12 +935,18 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
             std::memcpy(stage + (size_t)q * S + (size_t)l * Np, u + q * Ng + (int64_t)l2g[l] * Np, Np * sizeof(double));
         CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)q * S, stage + (size_t)q * S, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
+    if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, Ktot, h->dVinv, h->stream); ++h->launches; }  // owned + halo elements
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
 void stateToHost(dgb_handle* h, const double* src, double* u) {
     const int Np = h->Np;
     const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
+    if (h->bbMode) {  // Bernstein -> nodal into ACC (dead between stages: MODE_RK1 overwrites it), then copy from there
+        launchElementMatrix(src, h->ACC, S, Np, h->M.Kown, h->dV, h->stream);
+        ++h->launches;
+        src = h->ACC;
+    }
     if (!h->partitioned) {
         CUDA_CHECK(cudaMemcpyAsync(u, src, (size_t)4 * Ng * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -993,6 +1032,7 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
                     const double* phase, const double* duration) {
     return guarded([&] {
         if (!h || nsrc < 0 || (nsrc > 0 && (!offsets || !amp || !freq || !phase || !duration))) throw DgbException(DGB_ERR_ARG, "bad source arguments");
+        if (h->bbMode && nsrc > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support sources yet");
         std::vector<int32_t> off(1, 0), idx;
         for (int s = 0; s < nsrc; ++s) {
             for (int k = offsets[s]; k < offsets[s + 1]; ++k) {
@@ -1014,6 +1054,7 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
 int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
     return guarded([&] {
         if (!h || nprobe < 0 || (nprobe > 0 && !nodeIdx)) throw DgbException(DGB_ERR_ARG, "bad probe arguments");
+        if (h->bbMode && nprobe > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support probes yet");
         std::vector<int32_t> idx(nprobe);
         for (int j = 0; j < nprobe; ++j) idx[j] = localNode(h, nodeIdx[j], false);
         if (h->dProbeIdx) { cudaFree(h->dProbeIdx); h->dProbeIdx = nullptr; }
@@ -1041,6 +1082,7 @@ int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) 
 int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights) {
     return guarded([&] {
         if (!h || nrecv < 0 || (nrecv > 0 && (!el || !weights))) throw DgbException(DGB_ERR_ARG, "bad receiver arguments");
+        if (h->bbMode && nrecv > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support receivers yet");
         std::vector<int32_t> loc(nrecv);
         for (int j = 0; j < nrecv; ++j) {
             if (el[j] < 0 || el[j] >= h->Kglobal) throw DgbException(DGB_ERR_ARG, "receiver element out of range");
@@ -1125,7 +1167,23 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             } else if (value == 3) {
                 if (!h->ws.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no warp-specialised kernel for this dim/order/mean flow");
                 h->active = h->ws;
+            } else if (value == 4) {
+                if (!h->bbKernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
+                if (!h->srcAmp.empty() || h->nprobe > 0 || h->nrecv > 0)
+                    throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support sources / probes / receivers yet");
+                h->active = h->bbKernel;
             } else h->active = h->autoKernel();
+            // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes
+            const bool wantBB = h->active.launch && h->active.launch == h->bbKernel.launch;
+            if (wantBB != h->bbMode) {
+                finishExchange(h);
+                if (h->stateSet) {
+                    launchElementMatrix(h->U, h->U, h->M.stride, h->Np, h->M.Ktot, wantBB ? h->dVinv : h->dV, h->stream);
+                    ++h->launches;
+                    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                }
+                h->bbMode = wantBB;
+            }
         } else if (k == "overlap") {
             if (value < -1 || value > 2) throw DgbException(DGB_ERR_ARG, "overlap must be -1 (automatic), 0, 1 or 2");
             h->overlap = value;

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/dgb.h"
+#include "bb_ops.h"
 
 namespace dgb {
 
@@ -66,6 +67,12 @@ struct StageKernel {
 StageKernel selectGenericKernel(int dim, int order);
 StageKernel selectTiledKernel(int dim, int order);  // launch == nullptr if no tiled instance exists
 StageKernel selectWsKernel(int dim, int order);     // warp-specialised DMMA kernel, zero mean flow only (stage_ws.cu)
+StageKernel selectBBKernel(int dim, int order);     // Bernstein-Bezier sparse-operator kernel, tetrahedra (stage_bb.cu); the state holds Bernstein coefficients
+// permutation tables of the Bernstein kernel for one order (constant memory of the current device; they depend only on the
+// element's node numbering convention, so one copy per order serves every handle of the process)
+void setBBTables(int order, const bb::Tables& T);
+// y = Mat x per element and field over a whole state array (nodal <-> Bernstein conversion); in and out may alias
+void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s);
 
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);

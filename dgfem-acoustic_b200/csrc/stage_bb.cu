@@ -1,0 +1,208 @@
+// Bernstein-Bezier stage kernel for straight-sided tetrahedra (opt-in: dgb_set_option("kernel", 4)).
+//
+// The state arrays hold the BERNSTEIN COEFFICIENTS of the four fields (same layout u[eq][el*Np+n]; coefficient n belongs
+// to the Bernstein function whose index is N times the barycentric position of the mesh's node n; dgb_set_state /
+// dgb_get_state convert with V^-1 / V). In that basis the reference's dense per-element operators — the stiffness
+// quadrature of Mesh::getElStiffVector (Mesh.cpp:476-489), the inverse mass of eigen::linEq (utils.cpp:118-123) and the
+// face integrals of Mesh::precomputeFlux / getElFlux (Mesh.cpp:500-557) — collapse to the sparse closed forms of
+// bb_ops.h: ~6 kFLOP per element and stage at order 4 instead of ~36 k for the dense contractions, which moves the
+// order-4 stage from the FP64 roof to the HBM roof. CUDA cores only: there is nothing dense left.
+//
+// One CTA takes TE consecutive elements:
+//   1. coalesced load of the four fields' coefficients into shared memory;
+//   2. one task per (element, local face, face node): neighbour coefficient through the face-node map (the maps of the
+//      nodal scheme apply unchanged), numerical flux exactly as in the nodal kernels (dgb_device.cuh: faceFlux), stored as
+//      Fscale * (n.F(u-) - flux*) — the strong form, equal to the reference's weak form under exact quadrature;
+//   3. one thread per (element, FIELD): directional derivatives, elevation and the four face lifts of bb_ops.h entirely
+//      in registers (every index is a compile-time constant after unrolling), result back to shared memory;
+//   4. coalesced fused RK update, as in the other kernels.
+#include "dgb_internal.h"
+#include "dgb_device.cuh"
+#include "bb_ops.h"
+
+namespace dgb {
+
+namespace {
+
+__constant__ bb::Tables c_bbTables[bb::MAX_ORDER + 1];  // indexed by the order
+
+// smallest stride >= n (in doubles) for which the 16 lanes (4 elements x 4 fields) of a half-warp hit 16 distinct 8-byte
+// banks when lane (e, q) reads  q*stride + e*elemStride + const
+__host__ __device__ constexpr int conflictFreeStride(int n, int elemStride) {
+    for (int pad = 0; pad < 16; ++pad) {
+        const int s = n + pad;
+        bool ok = true;
+        unsigned seen = 0;
+        for (int q = 0; q < 4; ++q)
+            for (int e = 0; e < 4; ++e) {
+                const int b = (q * s + e * elemStride) % 16;
+                if (seen & (1u << b)) ok = false;
+                seen |= 1u << b;
+            }
+        if (ok) return s;
+    }
+    return n;
+}
+
+template <int P>
+struct BBCfg {
+    static constexpr int NP = bb::tet(P), NFP = bb::tri(P), NFL = 4 * NFP;
+#ifdef DGB_BB_TE
+    static constexpr int TE = DGB_BB_TE;  // elements per CTA
+#else
+    static constexpr int TE = 32;
+#endif
+    static constexpr int THREADS = 4 * TE;
+    static constexpr int SQ = conflictFreeStride(TE * NP, NP);    // field stride of the coefficient tile
+    static constexpr int SF = conflictFreeStride(TE * NFL, NFL);  // field stride of the face-input tile
+    static constexpr size_t SMEM = (size_t)4 * (SQ + SF) * sizeof(double);
+};
+
+template <int P>
+__global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M, StageArgs A) {
+    using C = BBCfg<P>;
+    constexpr int NP = C::NP, NFP = C::NFP, NFL = C::NFL, TE = C::TE;
+    extern __shared__ double smem[];
+    double* sQ = smem;                // [4][SQ]
+    double* sFl = smem + 4 * C::SQ;   // [4][SF]
+
+    const int tid = threadIdx.x;
+    const int e0 = A.eBegin + blockIdx.x * TE;
+    const int nE = min(TE, A.eEnd - e0);
+    const int64_t S = M.stride;
+    const Phys ph = makePhys(M);
+
+    // 1. own coefficients, coalesced
+    for (int i = tid; i < nE * NP; i += C::THREADS) {
+        const int64_t g = (int64_t)e0 * NP + i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sQ[q * C::SQ + i] = A.yin[q * S + g];
+    }
+    __syncthreads();
+
+    // 2. face inputs of the lift: Fscale * (n.F(u-) - flux*)
+    for (int w = tid; w < nE * NFL; w += C::THREADS) {
+        const int el = w / NFL, r = w - el * NFL, lf = r / NFP, m = r - lf * NFP;
+        const int e = e0 + el;
+        const int flags = M.fflags[e * 4 + lf];
+        const int bc = flags & FLAG_BC_MASK;
+        const double* fg = M.fgeo + ((int64_t)e * 4 + lf) * 4;
+        const double n[3] = {fg[0], fg[1], fg[2]};
+        const double fscale = fg[3];
+        const int own = M.faceNodes[lf * NFP + m];
+        double qm[4], qp[4] = {0, 0, 0, 0}, fl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) qm[q] = sQ[q * C::SQ + el * NP + own];
+        if (bc == FACE_INTERIOR) {
+            const int nb = M.fnbr[e * 4 + lf];
+            const int nn = M.nbrMaps[(flags >> FLAG_MAP_SHIFT) * NFP + m];
+            const int64_t gi = (int64_t)nb * NP + nn;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) qp[q] = A.yin[q * S + gi];
+        }
+        faceFlux(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, n, ph, qm, qp, fl);
+        const double v0n = ph.v0[0] * n[0] + ph.v0[1] * n[1] + ph.v0[2] * n[2];
+        const double vn = n[0] * qm[1] + n[1] * qm[2] + n[2] * qm[3];
+        const double pr = qm[0] * ph.invRho;
+        sFl[0 * C::SF + el * NFL + r] = fscale * (v0n * qm[0] + ph.rc2 * vn - fl[0]);
+        sFl[1 * C::SF + el * NFL + r] = fscale * (v0n * qm[1] + n[0] * pr - fl[1]);
+        sFl[2 * C::SF + el * NFL + r] = fscale * (v0n * qm[2] + n[1] * pr - fl[2]);
+        sFl[3 * C::SF + el * NFL + r] = fscale * (v0n * qm[3] + n[2] * pr - fl[3]);
+    }
+    __syncthreads();
+
+    // 3. one thread per (element, field): sparse Bernstein operators in registers
+    {
+        const int el = tid >> 2, q = tid & 3;
+        if (el < nE) {
+            const int e = e0 + el;
+            const double* G = M.Ginv + (int64_t)e * 9;  // G[x*3+u] = d u_u / d x_x ; lambda_0 = 1 - u_0 - u_1 - u_2
+            double gl[4][3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                const double g0 = G[x * 3 + 0], g1 = G[x * 3 + 1], g2 = G[x * 3 + 2];
+                gl[0][x] = -(g0 + g1 + g2);
+                gl[1][x] = g0;
+                gl[2][x] = g1;
+                gl[3][x] = g2;
+            }
+            double* mine = sFl + q * C::SF + el * NFL;
+            const bool flow = ph.v0[0] != 0.0 || ph.v0[1] != 0.0 || ph.v0[2] != 0.0;
+            double out[NP];
+            const bb::Tables& T = c_bbTables[P];
+            bb::fieldRhs<P>(q, sQ + el * NP, C::SQ, mine, T, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
+            // the face inputs of this (element, field) are consumed: its slot now carries the result, mesh node order
+#pragma unroll
+            for (int i = 0; i < NP; ++i) mine[T.permC2G[i]] = out[i];
+        }
+    }
+    __syncthreads();
+
+    // 4. fused RK update, coalesced
+    for (int i = tid; i < nE * NP; i += C::THREADS) {
+        const int el = i / NP, nd = i - el * NP;
+        const int64_t g = (int64_t)e0 * NP + i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rkUpdate(A, q * S + g, sFl[q * C::SF + el * NFL + nd], sQ[q * C::SQ + i]);
+    }
+}
+
+template <int P>
+void launchBB(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
+    using C = BBCfg<P>;
+    const int nEl = A.eEnd - A.eBegin;
+    if (nEl <= 0) return;
+    static bool configured = false;  // one device per process
+    if (!configured) {
+        cudaFuncSetAttribute(stageBBKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        configured = true;
+    }
+    stageBBKernel<P><<<(nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s>>>(M, A);
+}
+
+// y = Mat x per element and field (nodal <-> Bernstein conversion of a whole state array); in and out may alias
+__global__ void __launch_bounds__(256) elementMatrixKernel(const double* in, double* out, int64_t stride, int Np, int K, const double* __restrict__ mat) {
+    extern __shared__ double sx[];  // [4][E*Np]
+    const int E = 256 / Np;
+    const int e0 = blockIdx.x * E;
+    const int nE = min(E, K - e0);
+    const int tid = threadIdx.x;
+    const bool active = tid < nE * Np;
+    const int64_t g = (int64_t)e0 * Np + tid;
+    if (active)
+        for (int q = 0; q < 4; ++q) sx[q * E * Np + tid] = in[q * stride + g];
+    __syncthreads();
+    if (!active) return;
+    const int el = tid / Np, n = tid - el * Np;
+    double acc[4] = {0, 0, 0, 0};
+    for (int m = 0; m < Np; ++m) {
+        const double a = mat[n * Np + m];
+        for (int q = 0; q < 4; ++q) acc[q] = fma(a, sx[q * E * Np + el * Np + m], acc[q]);
+    }
+    for (int q = 0; q < 4; ++q) out[q * stride + g] = acc[q];
+}
+
+}  // namespace
+
+StageKernel selectBBKernel(int dim, int order) {
+    StageKernel k;
+    if (dim != 3) return k;
+#define DGB_CASE(P) \
+    if (order == P) { k.launch = &launchBB<P>; k.name = "stage_bb<3," #P ">"; return k; }
+    DGB_CASE(2) DGB_CASE(3) DGB_CASE(4) DGB_CASE(5)
+#undef DGB_CASE
+    return k;
+}
+
+void setBBTables(int order, const bb::Tables& T) {
+    if (order < 0 || order > bb::MAX_ORDER) return;
+    cudaMemcpyToSymbol(c_bbTables, &T, sizeof(T), (size_t)order * sizeof(bb::Tables), cudaMemcpyHostToDevice);
+}
+
+void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s) {
+    if (K <= 0) return;
+    const int E = 256 / Np;
+    elementMatrixKernel<<<(K + E - 1) / E, 256, (size_t)4 * E * Np * sizeof(double), s>>>(in, out, stride, Np, K, mat);
+}
+
+}  // namespace dgb

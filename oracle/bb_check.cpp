@@ -97,12 +97,10 @@ void evalRhs(const dgb_desc& d, const Setup& S, const double* u, double* rhs) {
                 for (int q = 0; q < 4; ++q) dphi[q][lf * NFP + m] = Fs * (tr[q] - fl[q]);
             }
         }
-        const double* cols[4] = {&c[(size_t)el * NP], &c[Ntot + (size_t)el * NP], &c[2 * Ntot + (size_t)el * NP], &c[3 * Ntot + (size_t)el * NP]};
-        const double* const(&colsRef)[4] = cols;
         const double v0[3] = {d.v0[0], d.v0[1], d.v0[2]};
         for (int q = 0; q < 4; ++q) {
             double r[NP];
-            fieldRhs<N>(q, colsRef, dphi[q], S.T, gl, v0, flow, rc2, invRho, r);
+            fieldRhs<N>(q, &c[(size_t)el * NP], (int)Ntot, dphi[q], S.T, gl, v0, flow, rc2, invRho, r);
             for (int i = 0; i < NP; ++i) out[q * Ntot + (size_t)el * NP + S.T.permC2G[i]] = r[i];
         }
     }
