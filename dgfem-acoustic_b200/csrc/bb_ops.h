@@ -161,6 +161,51 @@ BB_HD void liftFace(const double (&x)[tri(N)], double (&out)[tet(N)]) {
 
 constexpr int MAX_ORDER = 6, MAX_NP = tet(MAX_ORDER), MAX_NFP = tri(MAX_ORDER);
 
+// ---- face inputs of the lift ---------------------------------------------------------------------------------------------
+// x = Fscale * (n.F(u-) - flux*) with the reference's numerical flux (interior: Mesh.cpp:519-527 with the penalty sign tau;
+// absorbing: RKR rows, Mesh.cpp:391-418, 652-667; reflecting: Mesh.cpp:616-648). By linearity it only needs
+//     a_q = q- - q+ (interior)   or   a_q = q- (boundary),     S = n . a_v :
+//   interior    n.F(a) / 2 - tau c0 a_q / 2
+//   reflecting  x_p = rho0 c0^2 S                          x_v = v0n S n
+//   absorbing   x_p = (v0n - c0/4) a_p + 3/4 rho0 c0^2 S   x_v = v0n a_v + n (3/4 a_p / rho0 - c0/4 S)
+// all of the form  x_p = app a_p + aps S,   x_vx = b a_vx + n_x (c a_p + d S)  with five face-constant coefficients.
+constexpr int BC_INTERIOR = 0, BC_ABSORBING = 1, BC_REFLECTING = 2;  // == FACE_* of dgb_internal.h
+struct FaceCoef {
+    double app, aps, b, c, d;
+};
+BB_HD FaceCoef faceCoef(int bc, double tau, double fscale, double v0n, double c0, double rho0) {
+    const double rc2 = rho0 * c0 * c0;
+    FaceCoef k;
+    if (bc == BC_INTERIOR) {
+        k.app = 0.5 * fscale * (v0n - tau * c0);
+        k.aps = 0.5 * fscale * rc2;
+        k.b = k.app;
+        k.c = 0.5 * fscale / rho0;
+        k.d = 0.0;
+    } else if (bc == BC_ABSORBING) {
+        k.app = fscale * (v0n - 0.25 * c0);
+        k.aps = 0.75 * fscale * rc2;
+        k.b = fscale * v0n;
+        k.c = 0.75 * fscale / rho0;
+        k.d = -0.25 * fscale * c0;
+    } else {
+        k.app = 0.0;
+        k.aps = fscale * rc2;
+        k.b = 0.0;
+        k.c = 0.0;
+        k.d = fscale * v0n;
+    }
+    return k;
+}
+BB_HD void faceInput(const FaceCoef& k, const double (&n)[3], const double (&a)[4], double (&x)[4]) {
+    const double S = n[0] * a[1] + n[1] * a[2] + n[2] * a[3];
+    const double g = k.c * a[0] + k.d * S;
+    x[0] = k.app * a[0] + k.aps * S;
+    x[1] = k.b * a[1] + n[0] * g;
+    x[2] = k.b * a[2] + n[1] * g;
+    x[3] = k.b * a[3] + n[2] * g;
+}
+
 // Permutations between the mesh's element-local numbering and the canonical orders above (built by bb_setup.h, passed
 // to the kernels by value)
 struct Tables {

@@ -52,19 +52,29 @@ struct BBCfg {
 #else
     static constexpr int TE = 32;
 #endif
-    static constexpr int THREADS = 4 * TE;
+    static constexpr int THREADS = 4 * TE;  // == (element, face) pairs == (element, field) pairs of a tile
     static constexpr int SQ = conflictFreeStride(TE * NP, NP);    // field stride of the coefficient tile
     static constexpr int SF = conflictFreeStride(TE * NFL, NFL);  // field stride of the face-input tile
-    static constexpr size_t SMEM = (size_t)4 * (SQ + SF) * sizeof(double);
+    static constexpr int FC = 8;                                  // doubles per (element, face): 5 coefficients + normal
+    static constexpr size_t SMEM = (size_t)(4 * (SQ + SF) + THREADS * FC) * sizeof(double) + (size_t)2 * THREADS * sizeof(int);
 };
+
+__device__ __forceinline__ void cpAsync8(double* smemDst, const double* gmemSrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmemSrc) : "memory");
+}
 
 template <int P>
 __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M, StageArgs A) {
     using C = BBCfg<P>;
     constexpr int NP = C::NP, NFP = C::NFP, NFL = C::NFL, TE = C::TE;
+    static_assert(bb::BC_INTERIOR == FACE_INTERIOR && bb::BC_ABSORBING == FACE_ABSORBING && bb::BC_REFLECTING == FACE_REFLECTING, "face codes");
     extern __shared__ double smem[];
-    double* sQ = smem;                // [4][SQ]
-    double* sFl = smem + 4 * C::SQ;   // [4][SF]
+    double* sQ = smem;                       // [4][SQ]   coefficients of the tile
+    double* sFl = smem + 4 * C::SQ;          // [4][SF]   face inputs of the lift, later the result
+    double* sFc = sFl + 4 * C::SF;           // [TE*4][8] per (element, face): app, aps, b, c, d, n
+    int* sNbr = reinterpret_cast<int*>(sFc + C::THREADS * C::FC);  // [TE*4] first coefficient of the neighbour element, -1 on the boundary
+    int* sMap = sNbr + C::THREADS;                                 // [TE*4] offset of the face-node map
 
     const int tid = threadIdx.x;
     const int e0 = A.eBegin + blockIdx.x * TE;
@@ -72,42 +82,52 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
     const int64_t S = M.stride;
     const Phys ph = makePhys(M);
 
-    // 1. own coefficients, coalesced
+    // 1. own coefficients: asynchronous copies, all in flight at once (coalesced, 8 bytes each: an element starts on an 8-byte boundary only)
     for (int i = tid; i < nE * NP; i += C::THREADS) {
         const int64_t g = (int64_t)e0 * NP + i;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sQ[q * C::SQ + i] = A.yin[q * S + g];
+        for (int q = 0; q < 4; ++q) cpAsync8(&sQ[q * C::SQ + i], &A.yin[q * S + g]);
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // 2. face inputs of the lift: Fscale * (n.F(u-) - flux*)
-    for (int w = tid; w < nE * NFL; w += C::THREADS) {
-        const int el = w / NFL, r = w - el * NFL, lf = r / NFP, m = r - lf * NFP;
-        const int e = e0 + el;
+    // 1b. one thread per (element, local face): the face-constant coefficients of the lift input (bb_ops.h), once per face
+    if (tid < 4 * nE) {
+        const int e = e0 + (tid >> 2), lf = tid & 3;
         const int flags = M.fflags[e * 4 + lf];
         const int bc = flags & FLAG_BC_MASK;
         const double* fg = M.fgeo + ((int64_t)e * 4 + lf) * 4;
-        const double n[3] = {fg[0], fg[1], fg[2]};
-        const double fscale = fg[3];
+        const double n0 = fg[0], n1 = fg[1], n2 = fg[2];
+        const double v0n = ph.v0[0] * n0 + ph.v0[1] * n1 + ph.v0[2] * n2;
+        const bb::FaceCoef k = bb::faceCoef(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, fg[3], v0n, ph.c0, ph.rho0);
+        double* fc = sFc + tid * C::FC;
+        fc[0] = k.app; fc[1] = k.aps; fc[2] = k.b; fc[3] = k.c; fc[4] = k.d; fc[5] = n0; fc[6] = n1; fc[7] = n2;
+        sNbr[tid] = bc == FACE_INTERIOR ? M.fnbr[e * 4 + lf] * NP : -1;
+        sMap[tid] = (flags >> FLAG_MAP_SHIFT) * NFP;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // 2. face inputs of the lift, one task per (element, local face, face node): jump against the neighbour's coefficient
+    //    (same face-node maps as the nodal scheme) or the own trace on a boundary face
+    for (int w = tid; w < nE * NFL; w += C::THREADS) {
+        const int el = w / NFL, r = w - el * NFL, lf = r / NFP, m = r - lf * NFP;
+        const int ef = el * 4 + lf;
+        const double* fc = sFc + ef * C::FC;
+        const bb::FaceCoef k = {fc[0], fc[1], fc[2], fc[3], fc[4]};
+        const double n[3] = {fc[5], fc[6], fc[7]};
         const int own = M.faceNodes[lf * NFP + m];
-        double qm[4], qp[4] = {0, 0, 0, 0}, fl[4];
+        double a[4], x[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) qm[q] = sQ[q * C::SQ + el * NP + own];
-        if (bc == FACE_INTERIOR) {
-            const int nb = M.fnbr[e * 4 + lf];
-            const int nn = M.nbrMaps[(flags >> FLAG_MAP_SHIFT) * NFP + m];
-            const int64_t gi = (int64_t)nb * NP + nn;
+        for (int q = 0; q < 4; ++q) a[q] = sQ[q * C::SQ + el * NP + own];
+        const int nb = sNbr[ef];
+        if (nb >= 0) {
+            const int64_t gi = (int64_t)nb + M.nbrMaps[sMap[ef] + m];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) qp[q] = A.yin[q * S + gi];
+            for (int q = 0; q < 4; ++q) a[q] -= A.yin[q * S + gi];
         }
-        faceFlux(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, n, ph, qm, qp, fl);
-        const double v0n = ph.v0[0] * n[0] + ph.v0[1] * n[1] + ph.v0[2] * n[2];
-        const double vn = n[0] * qm[1] + n[1] * qm[2] + n[2] * qm[3];
-        const double pr = qm[0] * ph.invRho;
-        sFl[0 * C::SF + el * NFL + r] = fscale * (v0n * qm[0] + ph.rc2 * vn - fl[0]);
-        sFl[1 * C::SF + el * NFL + r] = fscale * (v0n * qm[1] + n[0] * pr - fl[1]);
-        sFl[2 * C::SF + el * NFL + r] = fscale * (v0n * qm[2] + n[1] * pr - fl[2]);
-        sFl[3 * C::SF + el * NFL + r] = fscale * (v0n * qm[3] + n[2] * pr - fl[3]);
+        bb::faceInput(k, n, a, x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sFl[q * C::SF + el * NFL + r] = x[q];
     }
     __syncthreads();
 

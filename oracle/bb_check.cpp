@@ -1,10 +1,9 @@
 // CPU checker of the Bernstein-Bezier path — TEST INFRASTRUCTURE ONLY (like everything under oracle/).
 //
-// Runs the product's own operator code (dgfem-acoustic_b200/csrc/bb_ops.h, bb_setup.h: the very templates the CUDA
-// kernel stage_bb.cu instantiates) on the host, element by element, around a plain restatement of the face-flux
-// formulas of the reference (Mesh.cpp:519-527 interior, :616-648 reflecting, :391-418 + :652-667 absorbing, the same
-// expressions as oracle.cpp's operator mode), so that tests can compare  V * rhs_Bernstein(V^-1 u)  with the oracle's
-// L(u) without a GPU. Nothing in the product links or loads this file.
+// Runs the product's own operator code (dgfem-acoustic_b200/csrc/bb_ops.h, bb_setup.h: the very templates and face
+// arithmetic the CUDA kernel stage_bb.cu instantiates) on the host, element by element, with the connectivity taken
+// straight from the desc (the reference's fNbrElId / fNToElNId), so that tests can compare  V * rhs_Bernstein(V^-1 u)
+// with the oracle's L(u) without a GPU. Nothing in the product links or loads this file.
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -64,37 +63,21 @@ void evalRhs(const dgb_desc& d, const Setup& S, const double* u, double* rhs) {
             const double v0n = d.v0[0] * n[0] + d.v0[1] * n[1] + d.v0[2] * n[2];
             int pos[MAX_NP];
             for (int m = 0; m < NFP; ++m) pos[S.faceNodes[(size_t)lf * NFP + m]] = m;
+            const double tau = d.fc * o * (side == 0 ? 1.0 : -1.0);
+            const int bc = !d.fIsBoundary[f] ? BC_INTERIOR : d.fBC[f] == 1 ? BC_REFLECTING : BC_ABSORBING;
+            const FaceCoef fk = faceCoef(bc, tau, Fs, v0n, d.c0, d.rho0);  // the kernel's own face arithmetic
             for (int k = 0; k < NFP; ++k) {
                 const int own = d.fNToElNId[((size_t)f * NFP + k) * 2 + side];
                 const int m = pos[own];
-                double qm[4], fl[4], tr[4];
-                for (int q = 0; q < 4; ++q) qm[q] = c[q * Ntot + (size_t)el * NP + own];
-                const double vn = n[0] * qm[1] + n[1] * qm[2] + n[2] * qm[3];
-                tr[0] = v0n * qm[0] + rc2 * vn;
-                for (int x = 0; x < 3; ++x) tr[1 + x] = v0n * qm[1 + x] + n[x] * qm[0] * invRho;
-                if (d.fIsBoundary[f]) {
-                    if (d.fBC[f] == 1) {
-                        double v[3];
-                        for (int x = 0; x < 3; ++x) v[x] = qm[1 + x] - vn * n[x];
-                        fl[0] = v0n * qm[0] + rc2 * (n[0] * v[0] + n[1] * v[1] + n[2] * v[2]);
-                        for (int x = 0; x < 3; ++x) fl[1 + x] = v0n * v[x] + n[x] * qm[0] * invRho;
-                    } else {
-                        fl[0] = 0.25 * d.c0 * qm[0] + 0.25 * d.c0 * d.c0 * d.rho0 * vn;
-                        for (int x = 0; x < 3; ++x) fl[1 + x] = 0.25 * n[x] * invRho * qm[0] + 0.25 * d.c0 * n[x] * vn;
-                    }
-                } else {
+                double a[4], x4[4];
+                for (int q = 0; q < 4; ++q) a[q] = c[q * Ntot + (size_t)el * NP + own];
+                if (bc == BC_INTERIOR) {
                     const int nb = d.fNbrElId[2 * (size_t)f + (1 - side)];
                     const int nbn = d.fNToElNId[((size_t)f * NFP + k) * 2 + (1 - side)];
-                    double qp[4];
-                    for (int q = 0; q < 4; ++q) qp[q] = c[q * Ntot + (size_t)nb * NP + nbn];
-                    const double tau = d.fc * o * (side == 0 ? 1.0 : -1.0);
-                    const double ps = qm[0] + qp[0];
-                    const double vns = n[0] * (qm[1] + qp[1]) + n[1] * (qm[2] + qp[2]) + n[2] * (qm[3] + qp[3]);
-                    fl[0] = 0.5 * (v0n * ps + rc2 * vns) + 0.5 * tau * d.c0 * (qm[0] - qp[0]);
-                    for (int x = 0; x < 3; ++x)
-                        fl[1 + x] = 0.5 * (v0n * (qm[1 + x] + qp[1 + x]) + n[x] * ps * invRho) + 0.5 * tau * d.c0 * (qm[1 + x] - qp[1 + x]);
+                    for (int q = 0; q < 4; ++q) a[q] -= c[q * Ntot + (size_t)nb * NP + nbn];
                 }
-                for (int q = 0; q < 4; ++q) dphi[q][lf * NFP + m] = Fs * (tr[q] - fl[q]);
+                faceInput(fk, n, a, x4);
+                for (int q = 0; q < 4; ++q) dphi[q][lf * NFP + m] = x4[q];
             }
         }
         const double v0[3] = {d.v0[0], d.v0[1], d.v0[2]};
