@@ -136,6 +136,12 @@ struct dgb_handle {
     bool bbMode = false;
     std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
     double *dV = nullptr, *dVinv = nullptr;
+    std::vector<double> hostV;       // [Np][Np], u_n = sum_m V[n][m] c_m (mesh node order)
+    // Bernstein twins of the probes / receivers (a nodal value is a weighted sum of the element's coefficients) and sources
+    int32_t* dProbeElBB = nullptr;
+    double *dProbeWBB = nullptr, *dRecvWBB = nullptr;
+    std::vector<int32_t> srcElOff;   // per source: its range in dSrcElList
+    int32_t *dSrcElList = nullptr, *dSrcNodeOff = nullptr, *dSrcNodeLocal = nullptr;
     StageKernel autoKernel() const { return ws.launch ? ws : tiled.launch ? tiled : generic; }
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
@@ -201,7 +207,7 @@ void freeHandle(dgb_handle* h) {
     }
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
-    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv);
+    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -488,6 +494,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                         if (S.faceNodes[(size_t)lf * Nfp + m] != H.faceNodes[(size_t)lf * Nfp + m]) throw std::runtime_error("face-node tables disagree");
                 setBBTables(d->order, S.T);
                 CUDA_CHECK(cudaGetLastError());
+                h->hostV = S.V;
                 h->dV = devUpload(S.V);
                 h->dVinv = devUpload(S.Vinv);
             } catch (const std::exception& e) {
@@ -832,12 +839,13 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
     }
     for (int step = step0; step < nsteps; ++step, t += dt) {
         if (h->nprobe > 0) {
-            launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
+            if (h->bbMode) launchGatherReceivers(h->U, h->M.stride, h->Np, h->dProbeElBB, h->dProbeWBB, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
+            else launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
             ++h->probeCount;
             ++h->launches;
         }
         if (h->nrecv > 0) {  // owned elements only: no halo value is read
-            launchGatherReceivers(h->U, h->M.stride, h->Np, h->dRecvEl, h->dRecvW, h->nrecv, h->dRecvRec + (size_t)h->recvCount * h->nrecv * 4, h->stream);
+            launchGatherReceivers(h->U, h->M.stride, h->Np, h->dRecvEl, h->bbMode ? h->dRecvWBB : h->dRecvW, h->nrecv, h->dRecvRec + (size_t)h->recvCount * h->nrecv * 4, h->stream);
             ++h->recvCount;
             ++h->launches;
         }
@@ -846,7 +854,9 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
             if (t < h->srcDur[s]) {  // solver.cpp:253-255, evaluated on the host in the reference's own expression
                 const double val = h->srcAmp[s] * sin(2 * M_PI * h->srcFreq[s] * t + h->srcPhase[s]);
                 const int n = h->srcOff[s + 1] - h->srcOff[s];
-                launchSetNodes(h->U, h->dSrcIdx + h->srcOff[s], n, val, h->stream);
+                if (h->bbMode) launchSetNodesBB(h->U, h->Np, h->dSrcElList + h->srcElOff[s], h->dSrcNodeOff + h->srcElOff[s], h->dSrcNodeLocal,
+                                                h->srcElOff[s + 1] - h->srcElOff[s] - 1 /* minus the closing entry */, val, h->dV, h->dVinv, h->stream);
+                else launchSetNodes(h->U, h->dSrcIdx + h->srcOff[s], n, val, h->stream);
                 if (n > 0) ++h->launches;
             }
         StageArgs A{};
@@ -1032,7 +1042,6 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
                     const double* phase, const double* duration) {
     return guarded([&] {
         if (!h || nsrc < 0 || (nsrc > 0 && (!offsets || !amp || !freq || !phase || !duration))) throw DgbException(DGB_ERR_ARG, "bad source arguments");
-        if (h->bbMode && nsrc > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support sources yet");
         std::vector<int32_t> off(1, 0), idx;
         for (int s = 0; s < nsrc; ++s) {
             for (int k = offsets[s]; k < offsets[s + 1]; ++k) {
@@ -1043,6 +1052,30 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
         }
         if (h->dSrcIdx) { cudaFree(h->dSrcIdx); h->dSrcIdx = nullptr; }
         h->dSrcIdx = devUpload(idx);
+        // the same node sets grouped by element, for the Bernstein mode (launchSetNodesBB): per source a run of elements, per
+        // element a run of local nodes. nodeOff holds one shared, ever-growing offset array (entry b and b+1 bracket element b;
+        // a closing entry after the last element of every source keeps the runs of two sources apart)
+        {
+            std::vector<int32_t> elList, nodeOff, nodeLocal, elOff(1, 0);
+            for (int s = 0; s < nsrc; ++s) {
+                std::vector<int32_t> nodes(idx.begin() + off[s], idx.begin() + off[s + 1]);
+                std::sort(nodes.begin(), nodes.end());
+                nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+                for (size_t k = 0; k < nodes.size(); ++k) {
+                    const int el = nodes[k] / h->Np;
+                    if (k == 0 || el != nodes[k - 1] / h->Np) { elList.push_back(el); nodeOff.push_back((int32_t)nodeLocal.size()); }
+                    nodeLocal.push_back(nodes[k] - el * h->Np);
+                }
+                elList.push_back(-1);  // closing entry: nodeOff[b + 1] of the source's last element
+                nodeOff.push_back((int32_t)nodeLocal.size());
+                elOff.push_back((int32_t)elList.size());
+            }
+            for (int32_t** p : {&h->dSrcElList, &h->dSrcNodeOff, &h->dSrcNodeLocal}) if (*p) { cudaFree(*p); *p = nullptr; }
+            h->dSrcElList = devUpload(elList);
+            h->dSrcNodeOff = devUpload(nodeOff);
+            h->dSrcNodeLocal = devUpload(nodeLocal);
+            h->srcElOff = elOff;
+        }
         h->srcOff = off;
         h->srcAmp.assign(amp, amp + nsrc);
         h->srcFreq.assign(freq, freq + nsrc);
@@ -1054,12 +1087,23 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
 int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
     return guarded([&] {
         if (!h || nprobe < 0 || (nprobe > 0 && !nodeIdx)) throw DgbException(DGB_ERR_ARG, "bad probe arguments");
-        if (h->bbMode && nprobe > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support probes yet");
         std::vector<int32_t> idx(nprobe);
         for (int j = 0; j < nprobe; ++j) idx[j] = localNode(h, nodeIdx[j], false);
         if (h->dProbeIdx) { cudaFree(h->dProbeIdx); h->dProbeIdx = nullptr; }
         if (h->dProbeRec) { cudaFree(h->dProbeRec); h->dProbeRec = nullptr; }
         h->dProbeIdx = devUpload(idx);
+        if (h->dProbeElBB) { cudaFree(h->dProbeElBB); h->dProbeElBB = nullptr; }
+        if (h->dProbeWBB) { cudaFree(h->dProbeWBB); h->dProbeWBB = nullptr; }
+        if (!h->hostV.empty()) {  // Bernstein mode: the nodal value is row n of V applied to the element's coefficients
+            std::vector<int32_t> elBB(nprobe);
+            std::vector<double> wBB((size_t)nprobe * h->Np, 0.0);
+            for (int j = 0; j < nprobe; ++j) {
+                elBB[j] = idx[j] >= 0 ? idx[j] / h->Np : -1;
+                if (idx[j] >= 0) std::copy_n(&h->hostV[(size_t)(idx[j] % h->Np) * h->Np], h->Np, &wBB[(size_t)j * h->Np]);
+            }
+            h->dProbeElBB = devUpload(elBB);
+            h->dProbeWBB = devUpload(wBB);
+        }
         h->nprobe = nprobe;
         h->probeCap = h->probeCount = 0;
     });
@@ -1082,7 +1126,6 @@ int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) 
 int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights) {
     return guarded([&] {
         if (!h || nrecv < 0 || (nrecv > 0 && (!el || !weights))) throw DgbException(DGB_ERR_ARG, "bad receiver arguments");
-        if (h->bbMode && nrecv > 0) throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support receivers yet");
         std::vector<int32_t> loc(nrecv);
         for (int j = 0; j < nrecv; ++j) {
             if (el[j] < 0 || el[j] >= h->Kglobal) throw DgbException(DGB_ERR_ARG, "receiver element out of range");
@@ -1096,6 +1139,14 @@ int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double*
         if (h->dRecvRec) { cudaFree(h->dRecvRec); h->dRecvRec = nullptr; }
         h->dRecvEl = devUpload(loc);
         h->dRecvW = devUpload(w);
+        if (h->dRecvWBB) { cudaFree(h->dRecvWBB); h->dRecvWBB = nullptr; }
+        if (!h->hostV.empty()) {  // Bernstein mode: sum_n w_n u_n = sum_m (V^T w)_m c_m
+            std::vector<double> wBB((size_t)nrecv * h->Np, 0.0);
+            for (int j = 0; j < nrecv; ++j)
+                for (int n = 0; n < h->Np; ++n)
+                    for (int m = 0; m < h->Np; ++m) wBB[(size_t)j * h->Np + m] += w[(size_t)j * h->Np + n] * h->hostV[(size_t)n * h->Np + m];
+            h->dRecvWBB = devUpload(wBB);
+        }
         h->nrecv = nrecv;
         h->recvCap = h->recvCount = 0;
     });
@@ -1169,8 +1220,6 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
                 h->active = h->ws;
             } else if (value == 4) {
                 if (!h->bbKernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
-                if (!h->srcAmp.empty() || h->nprobe > 0 || h->nrecv > 0)
-                    throw DgbException(DGB_ERR_UNSUPPORTED, "the Bernstein-Bezier kernel does not support sources / probes / receivers yet");
                 h->active = h->bbKernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes

@@ -71,6 +71,9 @@ StageKernel selectBBKernel(int dim, int order);     // Bernstein-Bezier sparse-o
 // permutation tables of the Bernstein kernel for one order (constant memory of the current device; they depend only on the
 // element's node numbering convention, so one copy per order serves every handle of the process)
 void setBBTables(int order, const bb::Tables& T);
+// hard source in Bernstein mode: elements elList[0..nEl) get the nodal value `value` at their local nodes nodeLocal[nodeOff[b]..nodeOff[b+1])
+void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal, int nEl, double value,
+                      const double* V, const double* Vinv, cudaStream_t s);
 // y = Mat x per element and field over a whole state array (nodal <-> Bernstein conversion); in and out may alias
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s);
 

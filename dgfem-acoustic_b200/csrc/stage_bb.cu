@@ -202,6 +202,32 @@ __global__ void __launch_bounds__(256) elementMatrixKernel(const double* in, dou
     for (int q = 0; q < 4; ++q) out[q * stride + g] = acc[q];
 }
 
+// Hard source in Bernstein mode (solver.cpp:248-256 sets NODAL values): one CTA per element that carries source nodes.
+// With delta_n = value - (V c)_n at the element's source nodes n (all taken from the coefficients before the update, the
+// overwrites of different nodes commute),  c += sum_n Vinv[:, n] delta_n  makes (V c)_n = value there and leaves every other
+// nodal value of the element unchanged.
+__global__ void __launch_bounds__(64) setNodesBBKernel(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal,
+                                                       double value, const double* __restrict__ V, const double* __restrict__ Vinv) {
+    __shared__ double c[bb::MAX_NP], delta[bb::MAX_NP];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int64_t base = (int64_t)elList[b] * Np;
+    const int n0 = nodeOff[b], nn = nodeOff[b + 1] - n0;
+    for (int m = t; m < Np; m += blockDim.x) c[m] = field[base + m];
+    __syncthreads();
+    for (int k = t; k < nn; k += blockDim.x) {
+        const int n = nodeLocal[n0 + k];
+        double cur = 0.0;
+        for (int m = 0; m < Np; ++m) cur = fma(V[n * Np + m], c[m], cur);
+        delta[k] = value - cur;
+    }
+    __syncthreads();
+    for (int m = t; m < Np; m += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nn; ++k) s = fma(Vinv[m * Np + nodeLocal[n0 + k]], delta[k], s);
+        field[base + m] = c[m] + s;
+    }
+}
+
 }  // namespace
 
 StageKernel selectBBKernel(int dim, int order) {
@@ -217,6 +243,11 @@ StageKernel selectBBKernel(int dim, int order) {
 void setBBTables(int order, const bb::Tables& T) {
     if (order < 0 || order > bb::MAX_ORDER) return;
     cudaMemcpyToSymbol(c_bbTables, &T, sizeof(T), (size_t)order * sizeof(bb::Tables), cudaMemcpyHostToDevice);
+}
+
+void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal, int nEl, double value,
+                      const double* V, const double* Vinv, cudaStream_t s) {
+    if (nEl > 0) setNodesBBKernel<<<nEl, 64, 0, s>>>(field, Np, elList, nodeOff, nodeLocal, value, V, Vinv);
 }
 
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s) {

@@ -87,14 +87,48 @@ def test_euler_and_switching_the_representation_with_a_resident_state(pkg, oracl
     eng.close()
 
 
-def test_unsupported_combinations_fail_loudly(pkg, mesh_dir):
-    mesh = _mesh(pkg, mesh_dir, "cube:2", 3, (0.0, 0.0, 0.0))
+def test_sources_probes_receivers_in_bernstein_mode(pkg, oracle_mod, mesh_dir):
+    """Hard source (nodal overwrite expressed on the coefficients), probes and receivers (V-weighted gathers)."""
+    model = pkg.Model.make_cube(4, -10.0, 10.0, 3)
+    cfg = pkg.Config()
+    cfg.add_source(2.0, 1.0, 0.0, 4.0, 10.0, 1500.0, 0.3, 1.0)
+    cfg.add_source(-5.0, -5.0, 2.0, 3.0, 4.0, 900.0, 0.0, 1.0)
+    mesh = pkg.Mesh(model, cfg)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(0.0, 0.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * 7))
+    offsets, idx = mesh.source_nodes()
+    assert len(idx) > 10
+    probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5), int(idx[3])], dtype=np.int32)
+    el, w = mesh.locate_receivers([(0.3, -0.2, 0.9), (4.0, 4.5, -3.0)])
+    steps = 20
+    u0 = _state(mesh, 5) * 1e-2
     eng = pkg.Engine(mesh, options={"kernel": 4})
-    with pytest.raises(pkg.DgbError):
-        eng.set_probes(np.array([0], dtype=np.int32))
+    eng.set_sources_from_config()
+    eng.set_probes(probes)
+    eng.set_receivers(el, w)
+    eng.set_state(u0)
+    eng.run(pkg.RUNGE_KUTTA, 0.0, steps)
+    got, rec_p, rec_r = eng.get_state(), eng.get_probes(steps), eng.get_receivers(steps)
+    orc = oracle_mod.Oracle(mesh)
+    orc.set_sources_from_config()
+    orc.set_receivers(el, w)
+    want = u0.copy()
+    _, ref_p = orc.run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, want, 0.0, steps, probes)
+    ref_r = orc.get_receivers(steps)
+    for q in range(4):
+        assert rel_l2(got[q], want[q]) < TOL
+        assert rel_l2(rec_p[:, :, q], ref_p[:, :, q]) < TOL
+        assert rel_l2(rec_r[:, :, q], ref_r[:, :, q]) < TOL
     eng.close()
+
+
+def test_unsupported_combinations_fail_loudly(pkg, mesh_dir):
     mesh2 = pkg.Mesh(pkg.Model.open_msh(mesh_dir / "square.msh", 2), pkg.Config())
     eng2 = pkg.Engine(mesh2)
     with pytest.raises(pkg.DgbError):
         eng2.set_option("kernel", 4)  # triangles: no Bernstein kernel
     eng2.close()
+    mesh6 = pkg.Mesh(pkg.Model.make_cube(2, -10.0, 10.0, 6), pkg.Config())
+    eng6 = pkg.Engine(mesh6)
+    with pytest.raises(pkg.DgbError):
+        eng6.set_option("kernel", 4)  # order 6: not instantiated
+    eng6.close()
