@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
     __syncthreads();
 
     // 2. face inputs of the lift, one task per (element, local face, face node): jump against the neighbour's coefficient
-    //    (same face-node maps as the nodal scheme) or the own trace on a boundary face
+    //    (same face-node maps as the nodal scheme) or the own trace on a boundary face; unrolled so that the gathers of
+    //    several tasks are in flight together
+#pragma unroll 3
     for (int w = tid; w < nE * NFL; w += C::THREADS) {
         const int el = w / NFL, r = w - el * NFL, lf = r / NFP, m = r - lf * NFP;
         const int ef = el * 4 + lf;
