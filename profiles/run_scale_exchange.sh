@@ -5,7 +5,7 @@
 N=${1:-2}; shift
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
-  DGB_TEST_P2P=1 timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -k direct_exchange 2>&1 | tail -5
+  DGB_TEST_P2P=1 DGB_TEST_BB=1 timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -k "direct_exchange or bernstein" 2>&1 | tail -5
 fi
 for X in 0 1; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29600 + X)) \

@@ -22,6 +22,7 @@ def main():
     out_dir, cells, order, steps, overlap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     flow = int(sys.argv[6]) if len(sys.argv) > 6 else 1  # 0: zero mean flow (warp-specialised kernel at orders 3, 4)
     exchange = int(sys.argv[7]) if len(sys.argv) > 7 else 0  # 1: direct peer-to-peer stores instead of ncclSend/ncclRecv
+    kernel = int(sys.argv[8]) if len(sys.argv) > 8 else 0      # 4: Bernstein-Bezier kernel (every rank switches)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -43,6 +44,8 @@ def main():
     probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5), mesh.nearest_node(-7, 3, -2)], dtype=np.int32)
     u0 = mesh.initial_condition()
     eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes(), options={"overlap": overlap})
+    if kernel:
+        eng.set_option("kernel", kernel)
     if exchange:
         eng.set_option("p2p_timeout_ms", 5000)
         eng.set_option("exchange", exchange)  # collective
