@@ -130,33 +130,60 @@ BB_HD void faceRaise(const double (&x)[tri(M)], double (&w)[tri(M + 1)]) {
     }
 }
 
-// layers l = L .. N of face J: out[layer l] += z_l,  z_{l+1} = -1/(l+2) E_{N-l-1}^T z_l
-template <int N, int J, int L>
+// ---- lift of one face, split into a face-independent part and the scatter into the element's coefficients --------------
+// face-local result: layer l (degree N-l, canonical 2D order) at offset layerOff(N, l); tet(N) values in all
+BB_HD constexpr int layerOff(int N, int l) {
+    int s = 0;
+    for (int k = 0; k < l; ++k) s += tri(N - k);
+    return s;
+}
+
+template <int N, int L>
 struct LiftLayers {
-    static BB_HD void run(const double (&z)[tri(N - L)], double (&out)[tet(N)]) {
+    // z = z_L (already scaled); stores it and descends: z_{l+1} = -1/(l+2) E_{N-l-1}^T z_l
+    static BB_HD void run(const double (&z)[tri(N - L)], double (&zl)[tet(N)]) {
         BB_UNROLL
-        for (int b1 = 0; b1 <= N - L; ++b1) {
-            BB_UNROLL
-            for (int b2 = 0; b2 <= N - L - b1; ++b2) {
-                const int i = layerIdx<N, J>(L, b1, b2);
-                out[i] = out[i] + z[fidx(N - L, b1, b2)];
-            }
-        }
+        for (int b = 0; b < tri(N - L); ++b) zl[layerOff(N, L) + b] = z[b];
         if constexpr (L < N) {
             double zn[tri(N - L - 1)];
             faceLower<N - L - 1>(z, -1.0 / (L + 2), zn);
-            LiftLayers<N, J, L + 1>::run(zn, out);
+            LiftLayers<N, L + 1>::run(zn, zl);
         }
     }
 };
 
-// out += LIFT_J x : x = Fscale * (n.F(u-) - flux*) as the Bernstein coefficients of the face polynomial, canonical 2D order
-template <int N, int J>
-BB_HD void liftFace(const double (&x)[tri(N)], double (&out)[tet(N)]) {
+// zl = all layers of LIFT x in face-local order: x = Fscale * (n.F(u-) - flux*) as the Bernstein coefficients of the face
+// polynomial (canonical 2D order). The same code for the four faces.
+template <int N>
+BB_HD void liftFaceLocal(const double (&x)[tri(N)], double (&zl)[tet(N)]) {
     double w[tri(N + 1)], y[tri(N)];
     faceRaise<N>(x, w);
     faceLower<N>(w, 1.0, y);
-    LiftLayers<N, J, 0>::run(y, out);
+    LiftLayers<N, 0>::run(y, zl);
+}
+
+// out[coefficient of layer l, 2D index b of face J] += zl[layer l][b]
+template <int N, int J>
+BB_HD void scatterAddFace(const double (&zl)[tet(N)], double (&out)[tet(N)]) {
+    BB_UNROLL
+    for (int l = 0; l <= N; ++l) {
+        BB_UNROLL
+        for (int b1 = 0; b1 <= N - l; ++b1) {
+            BB_UNROLL
+            for (int b2 = 0; b2 <= N - l - b1; ++b2) {
+                const int i = layerIdx<N, J>(l, b1, b2);
+                out[i] = out[i] + zl[layerOff(N, l) + fidx(N - l, b1, b2)];
+            }
+        }
+    }
+}
+
+// out += LIFT_J x
+template <int N, int J>
+BB_HD void liftFace(const double (&x)[tri(N)], double (&out)[tet(N)]) {
+    double zl[tet(N)];
+    liftFaceLocal<N>(x, zl);
+    scatterAddFace<N, J>(zl, out);
 }
 
 constexpr int MAX_ORDER = 6, MAX_NP = tet(MAX_ORDER), MAX_NFP = tri(MAX_ORDER);
@@ -230,8 +257,8 @@ BB_HD void liftFaceFrom(const double* dphi, const Tables& T, double (&out)[tet(N
 // Fscale * (n.F(u-) - flux*) in the mesh's (local face, face node) order, gl[j][x] = d lambda_j / d x.
 // (No array is indexed with a run-time value: everything stays in registers.)
 template <int N>
-BB_HD void fieldRhs(int q, const double* col0, int colStride, const double* dphi, const Tables& T, const double (&gl)[4][3],
-                    const double (&v0)[3], bool flow, double rc2, double invRho, double (&out)[tet(N)]) {
+BB_HD void fieldVolume(int q, const double* col0, int colStride, const Tables& T, const double (&gl)[4][3], const double (&v0)[3],
+                       bool flow, double rc2, double invRho, double (&out)[tet(N)]) {
     constexpr int NP = tet(N), ND = tet(N - 1);
     double t[ND];
     BB_UNROLL
@@ -261,6 +288,12 @@ BB_HD void fieldRhs(int q, const double* col0, int colStride, const double* dphi
     BB_UNROLL
     for (int i = 0; i < NP; ++i) out[i] = 0.0;
     elevateAdd<N>(t, -1.0, out);
+}
+
+template <int N>
+BB_HD void fieldRhs(int q, const double* col0, int colStride, const double* dphi, const Tables& T, const double (&gl)[4][3],
+                    const double (&v0)[3], bool flow, double rc2, double invRho, double (&out)[tet(N)]) {
+    fieldVolume<N>(q, col0, colStride, T, gl, v0, flow, rc2, invRho, out);
     liftFaceFrom<N, 0>(dphi, T, out);
     liftFaceFrom<N, 1>(dphi, T, out);
     liftFaceFrom<N, 2>(dphi, T, out);

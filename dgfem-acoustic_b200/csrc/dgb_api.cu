@@ -131,7 +131,7 @@ struct dgb_handle {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
     std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
     int stageEvUsed = 0;
-    StageKernel generic, tiled, ws, bbKernel, active;
+    StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, active;
     // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
     bool bbMode = false;
     std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
@@ -497,6 +497,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                 h->hostV = S.V;
                 h->dV = devUpload(S.V);
                 h->dVinv = devUpload(S.Vinv);
+                h->bbSeqKernel = selectBBKernel(dim, d->order, 1);
             } catch (const std::exception& e) {
                 h->bbWhyNot = e.what();
                 h->bbKernel = StageKernel{};
@@ -1218,12 +1219,12 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             } else if (value == 3) {
                 if (!h->ws.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no warp-specialised kernel for this dim/order/mean flow");
                 h->active = h->ws;
-            } else if (value == 4) {
+            } else if (value == 4 || value == 5) {  // 5: the face-sequential schedule of the same arithmetic
                 if (!h->bbKernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
-                h->active = h->bbKernel;
+                h->active = value == 4 ? h->bbKernel : h->bbSeqKernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes
-            const bool wantBB = h->active.launch && h->active.launch == h->bbKernel.launch;
+            const bool wantBB = h->active.launch && (h->active.launch == h->bbKernel.launch || h->active.launch == h->bbSeqKernel.launch);
             if (wantBB != h->bbMode) {
                 finishExchange(h);
                 if (h->stateSet) {

@@ -169,6 +169,152 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
     }
 }
 
+// ---- variant B: the four faces one after the other --------------------------------------------------------------------------
+// Same arithmetic, different schedule: the face inputs of ONE face at a time live in shared memory (15 instead of 60 values
+// per element and field at order 4), so a tile needs about half the shared memory and more CTAs fit an SM; the lift body is
+// shared by the four faces (a run-time loop; only the scatter into the element's coefficients is face-specific), which also
+// shrinks the code. Costs two more barriers per face. dgb_set_option("bb_variant", 1).
+template <int P>
+struct BBSeqCfg {
+    static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
+    static constexpr int TE = BBCfg<P>::TE, THREADS = 4 * TE;
+    static constexpr int SQ = conflictFreeStride(TE * NP, NP);
+    static constexpr int SX = conflictFreeStride(TE * NFP, NFP);  // field stride of the one-face input tile
+    static constexpr int FC = 8;
+    static constexpr size_t SMEM = (size_t)(4 * (SQ + SX) + THREADS * FC) * sizeof(double) + (size_t)2 * THREADS * sizeof(int);
+};
+
+template <int P>
+__global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceMesh M, StageArgs A) {
+    using C = BBSeqCfg<P>;
+    constexpr int NP = C::NP, NFP = C::NFP, TE = C::TE;
+    extern __shared__ double smem[];
+    double* sQ = smem;                       // [4][SQ]   coefficients of the tile, at the end the result
+    double* sX = smem + 4 * C::SQ;           // [4][SX]   lift inputs of the current face, canonical 2D order
+    double* sFc = sX + 4 * C::SX;            // [TE*4][8] per (element, local face): app, aps, b, c, d, n
+    int* sNbr = reinterpret_cast<int*>(sFc + C::THREADS * C::FC);
+    int* sMap = sNbr + C::THREADS;
+
+    const int tid = threadIdx.x;
+    const int e0 = A.eBegin + blockIdx.x * TE;
+    const int nE = min(TE, A.eEnd - e0);
+    const int64_t S = M.stride;
+    const Phys ph = makePhys(M);
+    const bb::Tables& T = c_bbTables[P];
+
+    for (int i = tid; i < nE * NP; i += C::THREADS) {
+        const int64_t g = (int64_t)e0 * NP + i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cpAsync8(&sQ[q * C::SQ + i], &A.yin[q * S + g]);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid < 4 * nE) {
+        const int e = e0 + (tid >> 2), lf = tid & 3;
+        const int flags = M.fflags[e * 4 + lf];
+        const int bc = flags & FLAG_BC_MASK;
+        const double* fg = M.fgeo + ((int64_t)e * 4 + lf) * 4;
+        const double n0 = fg[0], n1 = fg[1], n2 = fg[2];
+        const double v0n = ph.v0[0] * n0 + ph.v0[1] * n1 + ph.v0[2] * n2;
+        const bb::FaceCoef k = bb::faceCoef(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, fg[3], v0n, ph.c0, ph.rho0);
+        double* fc = sFc + tid * C::FC;
+        fc[0] = k.app; fc[1] = k.aps; fc[2] = k.b; fc[3] = k.c; fc[4] = k.d; fc[5] = n0; fc[6] = n1; fc[7] = n2;
+        sNbr[tid] = bc == FACE_INTERIOR ? M.fnbr[e * 4 + lf] * NP : -1;
+        sMap[tid] = (flags >> FLAG_MAP_SHIFT) * NFP;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // volume term of this thread's (element, field), in registers for the rest of the tile
+    const int elT = tid >> 2, qT = tid & 3;
+    const bool mineActive = elT < nE;
+    double out[NP];
+    if (mineActive) {
+        const double* G = M.Ginv + (int64_t)(e0 + elT) * 9;
+        double gl[4][3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double g0 = G[x * 3 + 0], g1 = G[x * 3 + 1], g2 = G[x * 3 + 2];
+            gl[0][x] = -(g0 + g1 + g2);
+            gl[1][x] = g0;
+            gl[2][x] = g1;
+            gl[3][x] = g2;
+        }
+        const bool flow = ph.v0[0] != 0.0 || ph.v0[1] != 0.0 || ph.v0[2] != 0.0;
+        bb::fieldVolume<P>(qT, sQ + elT * NP, C::SQ, T, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
+    }
+
+#pragma unroll 1
+    for (int J = 0; J < 4; ++J) {
+        const int lf = T.faceLf[J];
+        // lift inputs of face J: one task per (element, canonical face index b)
+        for (int w = tid; w < nE * NFP; w += C::THREADS) {
+            const int el = w / NFP, b = w - el * NFP;
+            const int m = T.facePos[J][b];  // position in the mesh's face-node list of local face lf
+            const int ef = el * 4 + lf;
+            const double* fc = sFc + ef * C::FC;
+            const bb::FaceCoef k = {fc[0], fc[1], fc[2], fc[3], fc[4]};
+            const double n[3] = {fc[5], fc[6], fc[7]};
+            const int own = M.faceNodes[lf * NFP + m];
+            double a[4], x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = sQ[q * C::SQ + el * NP + own];
+            const int nb = sNbr[ef];
+            if (nb >= 0) {
+                const int64_t gi = (int64_t)nb + M.nbrMaps[sMap[ef] + m];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] -= A.yin[q * S + gi];
+            }
+            bb::faceInput(k, n, a, x);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sX[q * C::SX + el * NFP + b] = x[q];
+        }
+        __syncthreads();
+        if (mineActive) {
+            double x[NFP], zl[NP];
+            const double* mine = sX + qT * C::SX + elT * NFP;
+#pragma unroll
+            for (int b = 0; b < NFP; ++b) x[b] = mine[b];
+            bb::liftFaceLocal<P>(x, zl);
+            switch (J) {  // warp-uniform
+                case 0: bb::scatterAddFace<P, 0>(zl, out); break;
+                case 1: bb::scatterAddFace<P, 1>(zl, out); break;
+                case 2: bb::scatterAddFace<P, 2>(zl, out); break;
+                default: bb::scatterAddFace<P, 3>(zl, out); break;
+            }
+        }
+        __syncthreads();  // sX is rewritten by the next face; after the last face nobody reads the coefficient tile any more
+    }
+
+    // result into the thread's own column of the coefficient tile (mesh node order)
+    if (mineActive) {
+        double* col = sQ + qT * C::SQ + elT * NP;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) col[T.permC2G[i]] = out[i];
+    }
+    __syncthreads();
+
+    // fused RK update, coalesced; the stage input is needed again only where the update reads it (first RK stage, Euler)
+    const bool needY = A.mode == MODE_RK1 || A.mode == MODE_EULER;
+    for (int i = tid; i < nE * NP; i += C::THREADS) {
+        const int64_t g = (int64_t)e0 * NP + i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rkUpdate(A, q * S + g, sQ[q * C::SQ + i], needY ? A.yin[q * S + g] : 0.0);
+    }
+}
+
+template <int P>
+void launchBBSeq(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
+    using C = BBSeqCfg<P>;
+    const int nEl = A.eEnd - A.eBegin;
+    if (nEl <= 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(stageBBSeqKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        configured = true;
+    }
+    stageBBSeqKernel<P><<<(nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s>>>(M, A);
+}
+
 template <int P>
 void launchBB(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = BBCfg<P>;
@@ -232,11 +378,15 @@ __global__ void __launch_bounds__(64) setNodesBBKernel(double* field, int Np, co
 
 }  // namespace
 
-StageKernel selectBBKernel(int dim, int order) {
+StageKernel selectBBKernel(int dim, int order, int variant) {
     StageKernel k;
     if (dim != 3) return k;
-#define DGB_CASE(P) \
-    if (order == P) { k.launch = &launchBB<P>; k.name = "stage_bb<3," #P ">"; return k; }
+#define DGB_CASE(P)                                                                                     \
+    if (order == P) {                                                                                   \
+        if (variant == 1) { k.launch = &launchBBSeq<P>; k.name = "stage_bb_seq<3," #P ">"; }            \
+        else { k.launch = &launchBB<P>; k.name = "stage_bb<3," #P ">"; }                                \
+        return k;                                                                                       \
+    }
     DGB_CASE(2) DGB_CASE(3) DGB_CASE(4) DGB_CASE(5)
 #undef DGB_CASE
     return k;

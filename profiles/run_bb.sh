@@ -1,11 +1,11 @@
 #!/bin/bash
 # Usage (under gpurun, 1 GPU): bash profiles/run_bb.sh
 # First hardware run of the Bernstein-Bezier kernel: its gated parity tests, then config 5 with it (--kernel 4) beside the
-# shipped warp-specialised kernel. Writes gpurun_out/bb_tests.log, gpurun_out/bb_bench.json, gpurun_out/ws_bench.json.
+# shipped warp-specialised kernel. Writes gpurun_out/bb_tests.log, gpurun_out/{bb,bbseq,ws}_bench.json.
 mkdir -p gpurun_out
 DGB_TEST_BB=1 timeout 900 python -m pytest tests/test_zz_bb_gpu.py -x -q 2>&1 | tee gpurun_out/bb_tests.log | tail -15
-for K in 4 3; do
-  name=$([ $K = 4 ] && echo bb || echo ws)
+for K in 4 5 3; do
+  name=$([ $K = 4 ] && echo bb || ([ $K = 5 ] && echo bbseq || echo ws))
   timeout 900 python bench.py --no-cpu-baseline --kernel $K > gpurun_out/${name}_bench.json 2> gpurun_out/${name}_bench.err
   python - gpurun_out/${name}_bench.json <<'PY'
 import json, sys

@@ -39,13 +39,14 @@ CASES = [("cube:3", 2, (0.0, 0.0, 0.0)), ("cube.msh", 3, (30.0, 10.0, 5.0)), ("c
          ("cube:2", 5, (0.0, 0.0, 0.0))]
 
 
+@pytest.mark.parametrize("variant", [4, 5])
 @pytest.mark.parametrize("name,order,v0", CASES)
-def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0):
+def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     mesh = _mesh(pkg, mesh_dir, name, order, v0)
     u0 = _state(mesh)
     orc = oracle_mod.Oracle(mesh)
-    eng = pkg.Engine(mesh, options={"kernel": 4})
-    assert eng.kernel_name == f"stage_bb<3,{order}>"
+    eng = pkg.Engine(mesh, options={"kernel": variant})
+    assert eng.kernel_name == (f"stage_bb<3,{order}>" if variant == 4 else f"stage_bb_seq<3,{order}>")
     rhs = eng.eval_rhs(u0)
     ref = orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u0)
     for q in range(4):
