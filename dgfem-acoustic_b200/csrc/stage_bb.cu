@@ -20,6 +20,16 @@
 #include "dgb_device.cuh"
 #include "bb_ops.h"
 
+// The CPU tests run THIS file through a small CUDA emulation (oracle/cuda_emu.h, oracle/bb_emulate.cpp: one OS thread per
+// CUDA thread, a barrier for __syncthreads); the few constructs a host compiler cannot take go through these macros.
+#ifdef DGB_EMULATE
+#define DGB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cuemu::dynamicSmem())
+#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) cuemu::launch(kernel, grid, block, smemBytes, __VA_ARGS__)
+#else
+#define DGB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) kernel<<<grid, block, smemBytes, stream>>>(__VA_ARGS__)
+#endif
+
 namespace dgb {
 
 namespace {
@@ -60,8 +70,22 @@ struct BBCfg {
 };
 
 __device__ __forceinline__ void cpAsync8(double* smemDst, const double* gmemSrc) {
+#ifdef DGB_EMULATE
+    *smemDst = *gmemSrc;
+#else
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmemSrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cpAsyncCommit() {
+#ifndef DGB_EMULATE
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cpAsyncWaitAll() {
+#ifndef DGB_EMULATE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
 }
 
 template <int P>
@@ -69,7 +93,7 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
     using C = BBCfg<P>;
     constexpr int NP = C::NP, NFP = C::NFP, NFL = C::NFL, TE = C::TE;
     static_assert(bb::BC_INTERIOR == FACE_INTERIOR && bb::BC_ABSORBING == FACE_ABSORBING && bb::BC_REFLECTING == FACE_REFLECTING, "face codes");
-    extern __shared__ double smem[];
+    DGB_DYNAMIC_SMEM(double, smem);
     double* sQ = smem;                       // [4][SQ]   coefficients of the tile
     double* sFl = smem + 4 * C::SQ;          // [4][SF]   face inputs of the lift, later the result
     double* sFc = sFl + 4 * C::SF;           // [TE*4][8] per (element, face): app, aps, b, c, d, n
@@ -88,7 +112,7 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
 #pragma unroll
         for (int q = 0; q < 4; ++q) cpAsync8(&sQ[q * C::SQ + i], &A.yin[q * S + g]);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cpAsyncCommit();
 
     // 1b. one thread per (element, local face): the face-constant coefficients of the lift input (bb_ops.h), once per face
     if (tid < 4 * nE) {
@@ -104,7 +128,7 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
         sNbr[tid] = bc == FACE_INTERIOR ? M.fnbr[e * 4 + lf] * NP : -1;
         sMap[tid] = (flags >> FLAG_MAP_SHIFT) * NFP;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cpAsyncWaitAll();
     __syncthreads();
 
     // 2. face inputs of the lift, one task per (element, local face, face node): jump against the neighbour's coefficient
@@ -188,7 +212,7 @@ template <int P>
 __global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceMesh M, StageArgs A) {
     using C = BBSeqCfg<P>;
     constexpr int NP = C::NP, NFP = C::NFP, TE = C::TE;
-    extern __shared__ double smem[];
+    DGB_DYNAMIC_SMEM(double, smem);
     double* sQ = smem;                       // [4][SQ]   coefficients of the tile, at the end the result
     double* sX = smem + 4 * C::SQ;           // [4][SX]   lift inputs of the current face, canonical 2D order
     double* sFc = sX + 4 * C::SX;            // [TE*4][8] per (element, local face): app, aps, b, c, d, n
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceM
 #pragma unroll
         for (int q = 0; q < 4; ++q) cpAsync8(&sQ[q * C::SQ + i], &A.yin[q * S + g]);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cpAsyncCommit();
     if (tid < 4 * nE) {
         const int e = e0 + (tid >> 2), lf = tid & 3;
         const int flags = M.fflags[e * 4 + lf];
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceM
         sNbr[tid] = bc == FACE_INTERIOR ? M.fnbr[e * 4 + lf] * NP : -1;
         sMap[tid] = (flags >> FLAG_MAP_SHIFT) * NFP;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cpAsyncWaitAll();
     __syncthreads();
 
     // volume term of this thread's (element, field), in registers for the rest of the tile
@@ -307,12 +331,14 @@ void launchBBSeq(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = BBSeqCfg<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
+#ifndef DGB_EMULATE
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(stageBBSeqKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         configured = true;
     }
-    stageBBSeqKernel<P><<<(nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s>>>(M, A);
+#endif
+    DGB_LAUNCH(stageBBSeqKernel<P>, (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }
 
 template <int P>
@@ -320,17 +346,19 @@ void launchBB(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = BBCfg<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
+#ifndef DGB_EMULATE
     static bool configured = false;  // one device per process
     if (!configured) {
         cudaFuncSetAttribute(stageBBKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         configured = true;
     }
-    stageBBKernel<P><<<(nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s>>>(M, A);
+#endif
+    DGB_LAUNCH(stageBBKernel<P>, (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }
 
 // y = Mat x per element and field (nodal <-> Bernstein conversion of a whole state array); in and out may alias
 __global__ void __launch_bounds__(256) elementMatrixKernel(const double* in, double* out, int64_t stride, int Np, int K, const double* __restrict__ mat) {
-    extern __shared__ double sx[];  // [4][E*Np]
+    DGB_DYNAMIC_SMEM(double, sx);  // [4][E*Np]
     const int E = 256 / Np;
     const int e0 = blockIdx.x * E;
     const int nE = min(E, K - e0);
@@ -394,18 +422,22 @@ StageKernel selectBBKernel(int dim, int order, int variant) {
 
 void setBBTables(int order, const bb::Tables& T) {
     if (order < 0 || order > bb::MAX_ORDER) return;
+#ifdef DGB_EMULATE
+    c_bbTables[order] = T;
+#else
     cudaMemcpyToSymbol(c_bbTables, &T, sizeof(T), (size_t)order * sizeof(bb::Tables), cudaMemcpyHostToDevice);
+#endif
 }
 
 void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal, int nEl, double value,
                       const double* V, const double* Vinv, cudaStream_t s) {
-    if (nEl > 0) setNodesBBKernel<<<nEl, 64, 0, s>>>(field, Np, elList, nodeOff, nodeLocal, value, V, Vinv);
+    if (nEl > 0) DGB_LAUNCH(setNodesBBKernel, nEl, 64, 0, s, field, Np, elList, nodeOff, nodeLocal, value, V, Vinv);
 }
 
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s) {
     if (K <= 0) return;
     const int E = 256 / Np;
-    elementMatrixKernel<<<(K + E - 1) / E, 256, (size_t)4 * E * Np * sizeof(double), s>>>(in, out, stride, Np, K, mat);
+    DGB_LAUNCH(elementMatrixKernel, (K + E - 1) / E, 256, (size_t)4 * E * Np * sizeof(double), s, in, out, stride, Np, K, mat);
 }
 
 }  // namespace dgb

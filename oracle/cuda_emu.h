@@ -1,0 +1,73 @@
+// Minimal CUDA execution emulation for CPU tests — TEST INFRASTRUCTURE ONLY.
+//
+// Lets a host compiler build and run a .cu file's kernels as they are written: one OS thread per CUDA thread of a block,
+// a barrier for __syncthreads(), blocks one after the other, `__shared__` arrays as function-level statics, dynamic shared
+// memory as one buffer per launch. No warps, no memory model, no asynchrony: it checks index logic and arithmetic of a
+// kernel, not its CUDA-specific behaviour. The kernel source cooperates through three macros (DGB_EMULATE, DGB_DYNAMIC_SMEM,
+// DGB_LAUNCH — see csrc/stage_bb.cu).
+#pragma once
+#include <cuda_runtime.h>  // host-side declarations; makes __global__ / __device__ / __forceinline__ harmless for g++
+
+#include <pthread.h>
+
+#include <algorithm>
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#undef __shared__
+#define __shared__ static  // one copy for all threads; blocks run one after the other
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#ifndef __restrict__
+#define __restrict__
+#endif
+
+namespace cuemu {
+struct Idx {
+    unsigned x = 0, y = 0, z = 0;
+};
+struct State {
+    pthread_barrier_t barrier;
+    std::vector<double> smem;
+};
+inline State*& current() {
+    static State* s = nullptr;
+    return s;
+}
+inline void* dynamicSmem() { return current()->smem.data(); }
+inline void syncthreads() { pthread_barrier_wait(&current()->barrier); }
+}  // namespace cuemu
+
+static thread_local cuemu::Idx threadIdx, blockIdx;
+static cuemu::Idx blockDim, gridDim;
+
+#define __syncthreads() cuemu::syncthreads()
+inline double __dmul_rn(double a, double b) { return a * b; }
+using std::max;
+using std::min;
+
+namespace cuemu {
+template <typename Kernel, typename... Args>
+void launch(Kernel kernel, unsigned grid, unsigned block, size_t smemBytes, Args... args) {
+    State st;
+    st.smem.assign(smemBytes / sizeof(double) + 16, 0.0);
+    pthread_barrier_init(&st.barrier, nullptr, block);
+    current() = &st;
+    blockDim.x = block;
+    gridDim.x = grid;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < block; ++t)
+        pool.emplace_back([=, &st] {
+            threadIdx.x = t;
+            for (unsigned b = 0; b < grid; ++b) {
+                blockIdx.x = b;
+                kernel(args...);
+                pthread_barrier_wait(&st.barrier);  // the next block reuses the shared memory
+            }
+        });
+    for (auto& th : pool) th.join();
+    pthread_barrier_destroy(&st.barrier);
+    current() = nullptr;
+}
+}  // namespace cuemu
