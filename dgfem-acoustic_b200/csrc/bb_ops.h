@@ -108,7 +108,7 @@ BB_HD void faceLower(const double (&w)[tri(M + 1)], double scale, double (&z)[tr
         for (int b2 = 0; b2 <= M - b1; ++b2) {
             const int b0 = M - b1 - b2;
             const double s = (b0 + 1) * w[fidx(M + 1, b1, b2)] + (b1 + 1) * w[fidx(M + 1, b1 + 1, b2)] + (b2 + 1) * w[fidx(M + 1, b1, b2 + 1)];
-            z[fidx(M, b1, b2)] = scale * s;
+            z[fidx(M, b1, b2)] = scale == 1.0 ? s : scale * s;
         }
     }
 }
@@ -138,22 +138,30 @@ BB_HD constexpr int layerOff(int N, int l) {
     return s;
 }
 
+// cumulative layer factor: z_l = layerScale(l) * (E^T ... E^T y) with the unnormalised lowering operators
+BB_HD constexpr double layerScale(int l) {
+    double s = 1.0;
+    for (int k = 1; k <= l; ++k) s *= -1.0 / (k + 1);
+    return s;
+}
+
 template <int N, int L>
 struct LiftLayers {
-    // z = z_L (already scaled); stores it and descends: z_{l+1} = -1/(l+2) E_{N-l-1}^T z_l
+    // z = UNSCALED layer L (integer-coefficient sums only); stores it and descends with E_{N-L-1}^T. The factor
+    // layerScale(L) is applied by the scatter (one fused multiply-add instead of a multiply here and an add there).
     static BB_HD void run(const double (&z)[tri(N - L)], double (&zl)[tet(N)]) {
         BB_UNROLL
         for (int b = 0; b < tri(N - L); ++b) zl[layerOff(N, L) + b] = z[b];
         if constexpr (L < N) {
             double zn[tri(N - L - 1)];
-            faceLower<N - L - 1>(z, -1.0 / (L + 2), zn);
+            faceLower<N - L - 1>(z, 1.0, zn);
             LiftLayers<N, L + 1>::run(zn, zl);
         }
     }
 };
 
-// zl = all layers of LIFT x in face-local order: x = Fscale * (n.F(u-) - flux*) as the Bernstein coefficients of the face
-// polynomial (canonical 2D order). The same code for the four faces.
+// zl = all layers of LIFT x in face-local order, layer l still to be multiplied by layerScale(l): x = Fscale * (n.F(u-) - flux*)
+// as the Bernstein coefficients of the face polynomial (canonical 2D order). The same code for the four faces.
 template <int N>
 BB_HD void liftFaceLocal(const double (&x)[tri(N)], double (&zl)[tet(N)]) {
     double w[tri(N + 1)], y[tri(N)];
@@ -162,7 +170,7 @@ BB_HD void liftFaceLocal(const double (&x)[tri(N)], double (&zl)[tet(N)]) {
     LiftLayers<N, 0>::run(y, zl);
 }
 
-// out[coefficient of layer l, 2D index b of face J] += zl[layer l][b]
+// out[coefficient of layer l, 2D index b of face J] += layerScale(l) * zl[layer l][b]
 template <int N, int J>
 BB_HD void scatterAddFace(const double (&zl)[tet(N)], double (&out)[tet(N)]) {
     BB_UNROLL
@@ -172,7 +180,8 @@ BB_HD void scatterAddFace(const double (&zl)[tet(N)], double (&out)[tet(N)]) {
             BB_UNROLL
             for (int b2 = 0; b2 <= N - l - b1; ++b2) {
                 const int i = layerIdx<N, J>(l, b1, b2);
-                out[i] = out[i] + zl[layerOff(N, l) + fidx(N - l, b1, b2)];
+                const double v = zl[layerOff(N, l) + fidx(N - l, b1, b2)];
+                out[i] = l == 0 ? out[i] + v : out[i] + layerScale(l) * v;
             }
         }
     }
