@@ -184,12 +184,34 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
     }
     __syncthreads();
 
-    // 4. fused RK update, coalesced
-    for (int i = tid; i < nE * NP; i += C::THREADS) {
-        const int el = i / NP, nd = i - el * NP;
-        const int64_t g = (int64_t)e0 * NP + i;
+    // 4. fused RK update, coalesced; per field, all RK-register loads of a thread are issued before the first use (the tile's
+    //    latency is paid once, not once per entry)
+    {
+        constexpr int NIT = (TE * NP + C::THREADS - 1) / C::THREADS;
+        const bool rkRegs = A.mode == MODE_RK2 || A.mode == MODE_RK3 || A.mode == MODE_RK4;
+        const int cnt = nE * NP;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int64_t gq = q * S + (int64_t)e0 * NP;
+            double uv[NIT], av[NIT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rkUpdate(A, q * S + g, sFl[q * C::SF + el * NFL + nd], sQ[q * C::SQ + i]);
+            for (int k = 0; k < NIT; ++k) {
+                const int i = tid + k * C::THREADS;
+                uv[k] = av[k] = 0.0;
+                if (i < cnt) {
+                    uv[k] = rkRegs ? A.u[gq + i] : sQ[q * C::SQ + i];  // first stage / Euler: the stage input is the base state
+                    if (rkRegs) av[k] = A.acc[gq + i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int i = tid + k * C::THREADS;
+                if (i < cnt) {
+                    const int el = i / NP, nd = i - el * NP;
+                    rkApply(A, gq + i, sFl[q * C::SF + el * NFL + nd], uv[k], av[k]);
+                }
+            }
+        }
     }
 }
 
@@ -317,12 +339,32 @@ __global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceM
     }
     __syncthreads();
 
-    // fused RK update, coalesced; the stage input is needed again only where the update reads it (first RK stage, Euler)
-    const bool needY = A.mode == MODE_RK1 || A.mode == MODE_EULER;
-    for (int i = tid; i < nE * NP; i += C::THREADS) {
-        const int64_t g = (int64_t)e0 * NP + i;
+    // fused RK update, coalesced; per field, all global loads of a thread are issued before the first use. The stage input
+    // (overwritten in the tile by the result) is read again only where the update needs it: first RK stage, Euler.
+    {
+        constexpr int NIT = (TE * NP + C::THREADS - 1) / C::THREADS;
+        const bool rkRegs = A.mode == MODE_RK2 || A.mode == MODE_RK3 || A.mode == MODE_RK4;
+        const bool needY = A.mode == MODE_RK1 || A.mode == MODE_EULER;
+        const int cnt = nE * NP;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int64_t gq = q * S + (int64_t)e0 * NP;
+            double uv[NIT], av[NIT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rkUpdate(A, q * S + g, sQ[q * C::SQ + i], needY ? A.yin[q * S + g] : 0.0);
+            for (int k = 0; k < NIT; ++k) {
+                const int i = tid + k * C::THREADS;
+                uv[k] = av[k] = 0.0;
+                if (i < cnt) {
+                    if (rkRegs) { uv[k] = A.u[gq + i]; av[k] = A.acc[gq + i]; }
+                    else if (needY) uv[k] = A.yin[gq + i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int i = tid + k * C::THREADS;
+                if (i < cnt) rkApply(A, gq + i, sQ[q * C::SQ + i], uv[k], av[k]);
+            }
+        }
     }
 }
 
