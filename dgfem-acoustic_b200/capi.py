@@ -79,6 +79,7 @@ def load_front():
     lib.dgf_make_cube.restype = C.c_void_p
     lib.dgf_make_cube.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
     lib.dgf_model_free.argtypes = [C.c_void_p]
+    lib.dgf_warp_model.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.dgf_write_msh.argtypes = [C.c_void_p, C.c_char_p]
     lib.dgf_model_dimension.argtypes = [C.c_void_p]
     lib.dgf_parse_config.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(DgfConfig)]
@@ -176,6 +177,11 @@ class Model:
     @classmethod
     def make_cube(cls, n, lo=-10.0, hi=10.0, order=1):
         return cls(load_front().dgf_make_cube(int(n), float(lo), float(hi), int(order)))
+
+    def warp(self, amp, k):
+        """Curved stand-in geometry: every node moves by a smooth field (dgf_warp_model)."""
+        load_front().dgf_warp_model(self.h, float(amp), float(k))
+        return self
 
     @property
     def dimension(self):

@@ -105,6 +105,11 @@ extern "C" int dgf_write_msh(const dgf_model* mm, const char* path) {
 }
 
 extern "C" void dgf_model_free(dgf_model* m) { delete m; }
+extern "C" int dgf_warp_model(dgf_model* m, double amp, double k) {
+    if (!m) return -1;
+    gml::warp(m->m, amp, k);
+    return 0;
+}
 extern "C" int dgf_model_dimension(const dgf_model* m) { return m ? m->m.dimension() : -1; }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,10 +310,18 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
             re.gradBasis(&q.pts[4 * g], &M->elUGradBasisFct[(size_t)g * Np * 3]);
             M->elWeight[g] = q.pts[4 * g + 3];
         }
-        M->elJacobian.resize((size_t)K * 9);
-        M->elJacobianDet.resize(K);
-        for (int el = 0; el < K; ++el)
-            gml::affineJacobian(gm, dim, &M->elNodeTags[(size_t)el * Np], &M->elJacobian[(size_t)el * 9], M->elJacobianDet[el]);
+        // straight-sided meshes: one Jacobian per element / face (compressed, nGeom = 1); curved ones: one per
+        // integration point, the reference's own layout (Mesh.h:37-42, 52-54, 70, 88)
+        const bool curved = gm.curved;
+        const int gE = curved ? nG : 1;
+        M->elJacobian.resize((size_t)K * gE * 9);
+        M->elJacobianDet.resize((size_t)K * gE);
+        for (int el = 0; el < K; ++el) {
+            if (!curved) { gml::affineJacobian(gm, dim, &M->elNodeTags[(size_t)el * Np], &M->elJacobian[(size_t)el * 9], M->elJacobianDet[el]); continue; }
+            for (int g = 0; g < nG; ++g)
+                gml::isoJacobian(gm, dim, order, &M->elNodeTags[(size_t)el * Np], &q.pts[4 * g], &M->elJacobian[((size_t)el * nG + g) * 9],
+                                 M->elJacobianDet[(size_t)el * nG + g]);
+        }
         M->nodeCoords.resize((size_t)K * Np * 3);
         for (size_t n = 0; n < (size_t)K * Np; ++n) std::copy(gm.node(M->elNodeTags[n]), gm.node(M->elNodeTags[n]) + 3, &M->nodeCoords[3 * n]);
 
@@ -363,24 +376,37 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
             M->fWeight[g] = qf.pts[4 * g + 3];
         }
         if (fDim > 0) rf.gradBasis(&qf.pts[0], fUGrad0.data());
-        M->fNormal.resize((size_t)F * 3);
-        M->fJacobianDet.resize(F);
+        const int gF = curved ? nGf : 1;
+        M->fNormal.resize((size_t)F * gF * 3);
+        M->fJacobianDet.resize((size_t)F * gF);
+        std::vector<double> fUGrad((size_t)Nfp * 3);
         for (int f = 0; f < F; ++f) {
-            double jac[9], det, n[3] = {1, 0, 0};
-            gml::affineJacobian(gm, fDim, &M->fNodeTags[(size_t)f * Nfp], jac, det);
-            M->fJacobianDet[f] = det;
-            if (fDim == 1) {
-                double g0[3], zdir[3] = {0, 0, -1};
-                solveJT(jac, dim, &fUGrad0[0], g0);
-                cross3(g0, zdir, n);  // Mesh.cpp:174-175 (the g>0 flip at :176-179 only re-aligns with this direction)
-            } else if (fDim == 2) {
-                double g0[3], g1[3];
-                solveJT(jac, dim, &fUGrad0[0], g0);
-                solveJT(jac, dim, &fUGrad0[3], g1);
-                cross3(g0, g1, n);  // Mesh.cpp:183
+            double first0[3] = {0, 0, 0};  // physical gradient of face basis function 0 at the first point (Mesh.cpp:176)
+            for (int g = 0; g < gF; ++g) {
+                double jac[9], det, n[3] = {1, 0, 0};
+                if (!curved) gml::affineJacobian(gm, fDim, &M->fNodeTags[(size_t)f * Nfp], jac, det);
+                else {
+                    gml::isoJacobian(gm, fDim, order, &M->fNodeTags[(size_t)f * Nfp], &qf.pts[4 * g], jac, det);
+                    if (fDim > 0) rf.gradBasis(&qf.pts[4 * g], fUGrad.data());
+                }
+                const double* ug = curved ? fUGrad.data() : fUGrad0.data();
+                M->fJacobianDet[(size_t)f * gF + g] = det;
+                if (fDim == 1) {
+                    double g0[3], zdir[3] = {0, 0, -1};
+                    solveJT(jac, dim, &ug[0], g0);
+                    cross3(g0, zdir, n);  // Mesh.cpp:174-175
+                    if (g == 0) std::copy(g0, g0 + 3, first0);
+                    else if (dot3(g0, first0) < 0) for (int x = 0; x < 3; ++x) n[x] = -n[x];  // Mesh.cpp:176-179
+                } else if (fDim == 2) {
+                    double g0[3], g1[3];
+                    solveJT(jac, dim, &ug[0], g0);
+                    solveJT(jac, dim, &ug[3], g1);
+                    cross3(g0, g1, n);  // Mesh.cpp:183
+                    if (g != 0 && dot3(&M->fNormal[(size_t)f * gF * 3], n) < 0) for (int x = 0; x < 3; ++x) n[x] = -n[x];  // Mesh.cpp:184-187
+                }
+                double nn = std::sqrt(dot3(n, n));
+                for (int x = 0; x < 3; ++x) M->fNormal[((size_t)f * gF + g) * 3 + x] = n[x] / nn;
             }
-            double nn = std::sqrt(dot3(n, n));
-            for (int x = 0; x < 3; ++x) M->fNormal[(size_t)f * 3 + x] = n[x] / nn;
         }
 
         // ---- face node -> element node maps (Mesh.cpp:253-263) ----
@@ -412,7 +438,7 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
             for (int x = 0; x < 3; ++x) bary[x] /= nv;
             for (int lf = 0; lf < Nf; ++lf) {
                 const double* xn = gm.node(M->elNodeTags[(size_t)el * Np + re.faceNodes[lf * Nfp]]);
-                const double* nf = &M->fNormal[(size_t)M->elFId[(size_t)el * Nf + lf] * 3];
+                const double* nf = &M->fNormal[(size_t)M->elFId[(size_t)el * Nf + lf] * gF * 3];  // fNormal(f, 0), Mesh.cpp:287
                 double dp = 0.0;
                 for (int x = 0; x < 3; ++x) dp += (xn[x] - bary[x]) * nf[x];
                 M->elFOrientation[(size_t)el * Nf + lf] = dp >= 0 ? 1 : -1;
@@ -429,7 +455,7 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
             for (int lf = 0; lf < Nf; ++lf)
                 if (M->elFId[(size_t)el * Nf + lf] == f) {
                     const int o = M->elFOrientation[(size_t)el * Nf + lf];
-                    for (int x = 0; x < 3; ++x) M->fNormal[(size_t)f * 3 + x] *= o;
+                    for (int x = 0; x < 3 * gF; ++x) M->fNormal[(size_t)f * gF * 3 + x] *= o;  // every integration point, Mesh.cpp:341-345
                     M->elFOrientation[(size_t)el * Nf + lf] = 1;
                 }
         }
@@ -447,7 +473,7 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
         }
 
         d.dim = dim; d.order = order; d.Np = Np; d.Nfp = Nfp; d.Nf = Nf; d.K = K; d.F = F;
-        d.nG = nG; d.nGf = nGf; d.nGeomEl = 1; d.nGeomF = 1; d.fc = fc;
+        d.nG = nG; d.nGf = nGf; d.nGeomEl = gE; d.nGeomF = gF; d.fc = fc;
         d.elBasisFct = M->elBasisFct.data(); d.elUGradBasisFct = M->elUGradBasisFct.data(); d.elWeight = M->elWeight.data();
         d.fBasisFct = M->fBasisFct.data(); d.fWeight = M->fWeight.data();
         d.elJacobian = M->elJacobian.data(); d.elJacobianDet = M->elJacobianDet.data();

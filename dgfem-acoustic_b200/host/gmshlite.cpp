@@ -758,4 +758,58 @@ void affineJacobian(const Model& m, int dim, const int* v, double jac[9], double
     for (int x = 0; x < 3; ++x) { jac[3 + x] = b[x]; jac[6 + x] = c[x] / nc; }
 }
 
+// completion of the tangent vectors (rows 0..dim-1 of jac already set) and determinant, Gmsh's conventions as in affineJacobian
+static void completeJacobian(int dim, double jac[9], double& det) {
+    if (dim == 3) {
+        det = jac[0] * (jac[4] * jac[8] - jac[5] * jac[7]) - jac[1] * (jac[3] * jac[8] - jac[5] * jac[6]) + jac[2] * (jac[3] * jac[7] - jac[4] * jac[6]);
+        return;
+    }
+    if (dim == 2) {
+        double c[3] = {jac[1] * jac[5] - jac[2] * jac[4], jac[2] * jac[3] - jac[0] * jac[5], jac[0] * jac[4] - jac[1] * jac[3]};
+        det = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        for (int x = 0; x < 3; ++x) jac[6 + x] = c[x] / det;
+        return;
+    }
+    double a[3] = {jac[0], jac[1], jac[2]};
+    det = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    double b[3];
+    if ((std::fabs(a[0]) >= std::fabs(a[1]) && std::fabs(a[0]) >= std::fabs(a[2])) ||
+        (std::fabs(a[1]) >= std::fabs(a[0]) && std::fabs(a[1]) >= std::fabs(a[2]))) {
+        b[0] = a[1]; b[1] = -a[0]; b[2] = 0.0;
+    } else {
+        b[0] = 0.0; b[1] = a[2]; b[2] = -a[1];
+    }
+    double nb = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+    for (int x = 0; x < 3; ++x) b[x] /= nb;
+    double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    double nc = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    for (int x = 0; x < 3; ++x) { jac[3 + x] = b[x]; jac[6 + x] = c[x] / nc; }
+}
+
+void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const double* uvw, double jac[9], double& det) {
+    for (int i = 0; i < 9; ++i) jac[i] = 0.0;
+    if (dim == 0) { jac[0] = jac[4] = jac[8] = 1.0; det = 1.0; return; }
+    const RefElement& re = refElement(dim, order);
+    std::vector<double> dphi((size_t)re.np * 3);
+    re.gradBasis(uvw, dphi.data());
+    for (int n = 0; n < re.np; ++n) {
+        const double* xn = m.node(nodeTags[n]);
+        for (int u = 0; u < dim; ++u)
+            for (int x = 0; x < 3; ++x) jac[u * 3 + x] += xn[x] * dphi[3 * n + u];
+    }
+    completeJacobian(dim, jac, det);
+}
+
+void warp(Model& m, double amp, double k) {
+    const int dim = m.dimension();
+    for (int tag = 0; tag <= m.maxNodeTag; ++tag) {
+        double* x = &m.xyz[3 * (size_t)tag];
+        const double x0 = x[0], x1 = x[1], x2 = x[2];
+        x[0] = x0 + amp * std::sin(k * x1 + 0.3) * (dim >= 2 ? 1.0 : 0.0) + (dim == 3 ? 0.5 * amp * std::sin(k * x2 + 0.2) : 0.0);
+        if (dim >= 2) x[1] = x1 + amp * std::sin(k * (dim == 3 ? x2 : x0) + 0.7);
+        if (dim == 3) x[2] = x2 + amp * std::sin(k * x0 + 1.1);
+    }
+    m.curved = true;
+}
+
 }  // namespace gml

@@ -72,6 +72,7 @@ struct Model {
     std::map<std::pair<int, int>, std::string> physNames;  // (dim, physTag) -> name
     std::vector<Entity> entities;
     std::vector<ElemBlock> blocks;
+    bool curved = false;  // high-order nodes moved off the straight-sided positions (warp): Jacobians vary inside an element
 
     int dimension() const;  // highest dimension that carries elements
     std::vector<int> elementTypes(int dim) const;
@@ -97,5 +98,12 @@ Model makeCube(int n, double lo, double hi, int order, bool withBoundaryElements
 // completion for elements of dimension < 3; det as Gmsh defines it (signed for tets, a norm below).
 // All elements are straight-sided, so one Jacobian per element is returned (constant over the points).
 void affineJacobian(const Model& m, int dim, const int* vertexTags, double jac[9], double& det);
+// The same for an isoparametric (possibly curved) element of Lagrange order `order` at the parametric point uvw:
+// tangents d x / d u_u = sum_n x_n d phi_n / d u_u, then the same completion and determinant conventions.
+void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const double* uvw, double jac[9], double& det);
+// Smooth displacement of EVERY node, x += amp * (sin(k y + 0.3), sin(k z + 0.7), sin(k x + 1.1)) restricted to the model's
+// dimension (2D models stay in their plane): turns a straight-sided order-p mesh into a conforming curved isoparametric one
+// (the stand-in for meshing a curved geometry with `gmsh -order p`). Sets Model::curved.
+void warp(Model& m, double amp, double k);
 
 }  // namespace gml

@@ -52,6 +52,10 @@ dgf_model* dgf_open_msh(const char* path, int order);
 dgf_model* dgf_make_cube(int n, double lo, double hi, int order);
 /* writes the model as MSH 4.0 ASCII (the format of the reference's doc meshes), e.g. to feed the reference itself */
 int dgf_write_msh(const dgf_model* m, const char* path);
+/* Curved stand-in geometry: moves EVERY node by a smooth field of amplitude amp and wave number k, which
+ * turns the straight-sided order-p model into a conforming curved isoparametric one (what `gmsh -order p` produces along
+ * curved boundaries). dgf_mesh_build then stores one Jacobian / normal per integration point (nGeomEl = nG, nGeomF = nGf). */
+int dgf_warp_model(dgf_model* m, double amp, double k);
 void dgf_model_free(dgf_model* m);
 int dgf_model_dimension(const dgf_model* m);
 

@@ -36,6 +36,10 @@ void finalize() {}
 void open(const std::string& fileName) {
     g_model = gml::readMsh(fileName);
     if (const char* o = std::getenv("GMSHLITE_ORDER")) gml::elevate(g_model, std::atoi(o));
+    if (const char* w = std::getenv("GMSHLITE_WARP")) {  // "amp,k": the curved stand-in geometry (gml::warp), same as dgf_warp_model
+        double amp = 0, k = 0;
+        if (std::sscanf(w, "%lf,%lf", &amp, &k) == 2) gml::warp(g_model, amp, k);
+    }
 }
 namespace option { void setNumber(const std::string&, const double) {} }
 namespace logger {
@@ -86,17 +90,19 @@ void getJacobians(const int elementType, const std::string& integrationType, std
     jacobians.resize(ne * q.n * 9);
     determinants.resize(ne * q.n);
     points.resize(ne * q.n * 3);
-    std::vector<double> phi(lin.np);
+    std::vector<double> phi(g_model.curved ? re.np : lin.np);
     for (size_t e = 0; e < ne; ++e) {
         double jac[9], det;
-        gml::affineJacobian(g_model, dim, &nodes[e * re.np], jac, det);
+        if (!g_model.curved) gml::affineJacobian(g_model, dim, &nodes[e * re.np], jac, det);
         for (int g = 0; g < q.n; ++g) {
+            if (g_model.curved) gml::isoJacobian(g_model, dim, order, &nodes[e * re.np], &q.pts[4 * g], jac, det);  // per point
             std::copy(jac, jac + 9, &jacobians[(e * q.n + g) * 9]);
             determinants[e * q.n + g] = det;
-            lin.basis(&q.pts[4 * g], phi.data());
+            const gml::RefElement& map = g_model.curved ? re : lin;
+            map.basis(&q.pts[4 * g], phi.data());
             for (int x = 0; x < 3; ++x) {
                 double s = 0;
-                for (int v = 0; v < lin.np; ++v) s += phi[v] * g_model.node(nodes[e * re.np + v])[x];
+                for (int v = 0; v < map.np; ++v) s += phi[v] * g_model.node(nodes[e * re.np + v])[x];
                 points[(e * q.n + g) * 3 + x] = s;
             }
         }

@@ -71,3 +71,55 @@ def test_disk_p2_quadrupole_reflecting(pkg, oracle_mod, mesh_dir, tmp_path):
             for q in range(3):
                 assert rel_l2(u[q], ref[q]) < 1e-12, (mode, st, q)
             assert np.abs(u[3]).max() == 0.0 and np.abs(v[:, :, 2]).max() == 0.0
+
+
+CONF_CURVED = """timeStart=0
+timeEnd=0.00021
+timeStep=0.00002
+timeRate=0.0001
+elementType=Lagrange
+timeIntMethod=Runge-Kutta
+Absorbing = Reflecting
+numThreads=2
+v0_x = 8
+v0_y = -3
+v0_z = 0
+rho0 = 1.225
+c0 = 343
+initialCondtition1 = gaussian, -1,1,0,1,0.5
+saveFile=out
+"""
+
+
+@pytest.mark.parametrize("mesh_name,order,warp", [("square.msh", 3, (0.15, 0.9)), ("cube.msh", 2, (0.2, 0.4))])
+def test_curved_elements_faithful_oracle_equals_the_reference(pkg, oracle_mod, mesh_dir, tmp_path, mesh_name, order, warp):
+    """SURVEY §8 f3 groundwork: on a curved (warped isoparametric) mesh the reference keeps one Jacobian / normal per
+    integration point; the front end produces that layout (nGeomEl = nG, nGeomF = nGf) and the oracle's faithful mode —
+    the reference's own loops — reproduces the reference binary. (The collapsed operator form does not apply: the
+    quadrature is no longer exact and the element mass matrices differ.)"""
+    conf = tmp_path / "case.conf"
+    text = CONF_CURVED if mesh_name == "square.msh" else CONF_CURVED.replace("v0_z = 0", "v0_z = 2")
+    conf.write_text(text)
+    env = dict(os.environ, GMSHLITE_QUIET="1", GMSHLITE_ORDER=str(order), GMSHLITE_WARP=f"{warp[0]},{warp[1]}", OMP_NUM_THREADS="2")
+    subprocess.run([str(REF_BIN), str(mesh_dir / mesh_name), str(conf)], cwd=tmp_path, env=env, check=True, timeout=900)
+    P, V = read_view(tmp_path / "out.Pressure.bin"), read_view(tmp_path / "out.Velocity.bin")
+    model = pkg.Model.open_msh(mesh_dir / mesh_name, order).warp(*warp)
+    cfg = model.parse_config(conf)
+    mesh = pkg.Mesh(model, cfg)
+    assert mesh.desc.nGeomEl == mesh.desc.nG and mesh.desc.nGeomF == mesh.desc.nGf
+    det = mesh.elJacobianDet
+    assert (np.abs(det.max(axis=1) - det.min(axis=1)) > 1e-6 * np.abs(det).mean()).mean() > 0.9  # the elements really are curved
+    orc = oracle_mod.Oracle(mesh, threads=2)
+    u = mesh.initial_condition()
+    t, done = cfg.c.timeStart, 0
+    for (st, tt, p), (_, _, v) in zip(P, V):
+        t, _ = orc.run(oracle_mod.Oracle.FAITHFUL, pkg.RUNGE_KUTTA, u, t, st - done)
+        done = st
+        assert t == tt
+        v = v.reshape(mesh.K, mesh.Np, 3)
+        ref = [p.reshape(-1), v[:, :, 0].reshape(-1), v[:, :, 1].reshape(-1), v[:, :, 2].reshape(-1)]
+        for q in range(4):
+            if np.abs(ref[q]).max() == 0.0:
+                assert np.abs(u[q]).max() == 0.0
+            else:
+                assert rel_l2(u[q], ref[q]) < 1e-12, (st, q)
