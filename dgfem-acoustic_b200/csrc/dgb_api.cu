@@ -10,9 +10,11 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "bb_setup.h"
+#include "curved_setup.h"
 #include "dgb_internal.h"
 #include "partition.h"
 #include "tile_cfg.h"
@@ -135,6 +137,11 @@ struct dgb_handle {
     // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
     bool bbMode = false;
     std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
+    // curved (non-affine) meshes: the reference's own tables on the device + inverse element mass matrices; every
+    // element then goes through stage_curved.cu
+    bool curved = false;
+    CurvedMesh CM{};
+    std::vector<void*> curvedAllocs;
     double *dV = nullptr, *dVinv = nullptr;
     std::vector<double> hostV;       // [Np][Np], u_n = sum_m V[n][m] c_m (mesh node order)
     // Bernstein twins of the probes / receivers (a nodal value is a weighted sum of the element's coefficients) and sources
@@ -207,6 +214,7 @@ void freeHandle(dgb_handle* h) {
     }
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
+    for (void* p : h->curvedAllocs) F(p);
     F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
@@ -234,27 +242,6 @@ void validate(const dgb_desc* d) {
     if (!(d->nGeomEl == 1 || d->nGeomEl == d->nG) || !(d->nGeomF == 1 || d->nGeomF == d->nGf)) throw DgbException(DGB_ERR_ARG, "nGeomEl/nGeomF must be 1 or nG/nGf");
     if (d->Np > 255) throw DgbException(DGB_ERR_UNSUPPORTED, "more than 255 nodes per element");
     if (!(d->rho0 > 0) || !(d->c0 > 0)) throw DgbException(DGB_ERR_ARG, "rho0 and c0 must be positive");
-}
-
-// The hot path is written for straight-sided elements: every quadrature point of an element / face must carry
-// the same Jacobian / normal (curved geometry is SURVEY §8 f3).
-void checkAffine(const dgb_desc* d) {
-    if (d->nGeomEl > 1)
-        for (int el = 0; el < d->K; ++el)
-            for (int g = 1; g < d->nG; ++g) {
-                for (int k = 0; k < 9; ++k) {
-                    const double a = d->elJacobian[((size_t)el * d->nG) * 9 + k], b = d->elJacobian[((size_t)el * d->nG + g) * 9 + k];
-                    if (std::fabs(a - b) > 1e-11 * (std::fabs(a) + std::fabs(b) + 1e-300) + 1e-13)
-                        throw DgbException(DGB_ERR_UNSUPPORTED, "curved (non-affine) element " + std::to_string(el) + ": not supported by this engine");
-                }
-            }
-    if (d->nGeomF > 1)
-        for (int f = 0; f < d->F; ++f)
-            for (int g = 1; g < d->nGf; ++g)
-                for (int k = 0; k < 3; ++k) {
-                    const double a = d->fNormal[((size_t)f * d->nGf) * 3 + k], b = d->fNormal[((size_t)f * d->nGf + g) * 3 + k];
-                    if (std::fabs(a - b) > 1e-11) throw DgbException(DGB_ERR_UNSUPPORTED, "curved face " + std::to_string(f) + ": not supported by this engine");
-                }
 }
 
 struct HostOperators {
@@ -338,7 +325,10 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         throw DgbException(DGB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
-    checkAffine(d);
+    const bool curved = isCurved(d);
+    if (curved && nranks > 1) throw DgbException(DGB_ERR_UNSUPPORTED, "curved (non-affine) elements are not supported on partitioned handles yet");
+    if (curved && (d->nGeomEl != d->nG || d->nGeomF != d->nGf))
+        throw DgbException(DGB_ERR_ARG, "curved elements need one Jacobian / normal per integration point (nGeomEl == nG, nGeomF == nGf)");
     HostOperators H = buildOperators(d);
 
     dgb_handle* h = new dgb_handle;
@@ -474,9 +464,38 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         if (!h->generic.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no stage kernel for this dim/order");
         if (M.v0[0] == 0.0 && M.v0[1] == 0.0 && M.v0[2] == 0.0) h->ws = selectWsKernel(dim, d->order);
         h->active = h->autoKernel();
+        if (curved) {
+            // nothing collapses on curved elements: upload the reference's own tables and the inverse element mass matrices
+            h->curved = true;
+            CurvedMesh& C = h->CM;
+            auto up = [&](const auto* src, size_t n) {
+                typedef typename std::remove_const<typename std::remove_pointer<decltype(src)>::type>::type T;
+                T* p = devAlloc<T>(n);
+                h->curvedAllocs.push_back(p);
+                CUDA_CHECK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+                return (const T*)p;
+            };
+            const size_t nG = d->nG, nGf = d->nGf, F = d->F;
+            C.dim = dim; C.Np = Np; C.Nfp = Nfp; C.Nf = Nf; C.K = K; C.F = d->F; C.nG = d->nG; C.nGf = d->nGf; C.fc = d->fc;
+            C.elBasis = up(d->elBasisFct, nG * Np); C.elUGrad = up(d->elUGradBasisFct, nG * Np * 3); C.elWeight = up(d->elWeight, nG);
+            C.fBasis = up(d->fBasisFct, nGf * Nfp); C.fWeight = up(d->fWeight, nGf);
+            C.elJac = up(d->elJacobian, (size_t)K * nG * 9); C.elDet = up(d->elJacobianDet, (size_t)K * nG);
+            C.fNormal = up(d->fNormal, F * nGf * 3); C.fDet = up(d->fJacobianDet, F * nGf);
+            C.elFId = up(d->elFId, (size_t)K * Nf); C.elFOrientation = up(d->elFOrientation, (size_t)K * Nf);
+            C.fNbrElId = up(d->fNbrElId, F * 2); C.fNToElNId = up(d->fNToElNId, F * Nfp * 2);
+            C.fIsBoundary = up(d->fIsBoundary, F); C.fBC = up(d->fBC, F);
+            const std::vector<double> Minv = curvedInverseMass(d);
+            C.Minv = up(Minv.data(), Minv.size());
+            C.c0 = d->c0; C.rho0 = d->rho0; C.v0[0] = d->v0[0]; C.v0[1] = d->v0[1]; C.v0[2] = d->v0[2];
+            C.stride = M.stride;
+            h->ws = h->tiled = StageKernel{};
+            h->active = h->generic;  // placeholder entry (launchStage dispatches on h->curved)
+            h->active.name = "stage_curved";
+        }
         // Bernstein-Bezier path (opt-in): conversion matrices, permutation tables, self-check of the closed-form lift
-        h->bbKernel = selectBBKernel(dim, d->order);
-        if (!h->bbKernel.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra, orders 2..5)";
+        h->bbKernel = curved ? StageKernel{} : selectBBKernel(dim, d->order);
+        if (curved) h->bbWhyNot = "curved elements";
+        else if (!h->bbKernel.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra, orders 2..5)";
         else {
             try {
                 const bb::Setup S = bb::buildSetup(d);
@@ -533,7 +552,8 @@ void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     A.smReserve = (h->partitioned && h->exchangeMode == 0 && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches beside NCCL kernels only
     const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
     if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
-    h->active.launch(h->M, A, h->stream);
+    if (h->curved) launchCurved(h->CM, A, h->stream);
+    else h->active.launch(h->M, A, h->stream);
     if (t) { cudaEventRecord(h->stageEv[h->stageEvUsed + 1], h->stream); h->stageEvUsed += 2; }
     ++h->launches;
 }
@@ -1212,6 +1232,10 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
         if (!h || !key) throw DgbException(DGB_ERR_ARG, "null argument");
         const std::string k(key);
         if (k == "kernel") {
+            if (h->curved) {
+                if (value != 0) throw DgbException(DGB_ERR_UNSUPPORTED, "curved meshes run the curved-element kernel only");
+                return;
+            }
             if (value == 1) h->active = h->generic;
             else if (value == 2) {
                 if (!h->tiled.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no tiled kernel for this dim/order");

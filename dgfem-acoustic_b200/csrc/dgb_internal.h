@@ -77,6 +77,8 @@ void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_
 // y = Mat x per element and field over a whole state array (nodal <-> Bernstein conversion); in and out may alias
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s);
 
+struct CurvedMesh;  // curved_setup.h
+void launchCurved(const CurvedMesh& C, const StageArgs& A, cudaStream_t s);  // stage_curved.cu: every element through the reference's own loops
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);
 void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s);

@@ -34,7 +34,7 @@ typedef struct dgb_handle dgb_handle;
 typedef enum dgb_status {
     DGB_OK = 0,
     DGB_ERR_ARG = -1,         /* null pointer / inconsistent sizes */
-    DGB_ERR_UNSUPPORTED = -2, /* curved (non-affine) geometry, unknown element, order > 6 ... */
+    DGB_ERR_UNSUPPORTED = -2, /* unknown element, order > 6, curved geometry on a partitioned handle ... */
     DGB_ERR_CUDA = -3,        /* CUDA runtime / no device */
     DGB_ERR_NCCL = -4,
     DGB_ERR_STATE = -5        /* call order (e.g. run before set_state) */
@@ -84,8 +84,10 @@ typedef struct dgb_desc {
 } dgb_desc;
 
 /* ---- life cycle -------------------------------------------------------------------------------------- */
-/* Builds the reference-element operators (Dw^u, LIFT), checks that the geometry is affine, converts to the
- * device layout and uploads everything once. Single GPU (current CUDA device). */
+/* Builds the reference-element operators (Dw^u, LIFT), converts to the device layout and uploads everything once.
+ * Straight-sided meshes run the collapsed operator kernels; a mesh with curved elements (Jacobians / normals that vary
+ * between the integration points; the desc must then use the reference layout nGeomEl == nG, nGeomF == nGf) runs the
+ * reference's own quadrature loops on the device (csrc/stage_curved.cu). Single GPU (current CUDA device). */
 int dgb_create(const dgb_desc* desc, dgb_handle** out);
 
 /* Multi-GPU: every rank passes the SAME global desc plus elPart[K] (owner rank of every element); the handle

@@ -1,0 +1,73 @@
+// Runs the curved-element CUDA kernel (dgfem-acoustic_b200/csrc/stage_curved.cu, the file itself) on the CPU through
+// cuda_emu.h — TEST INFRASTRUCTURE ONLY. The CurvedMesh is what dgb_create uploads for a curved mesh: the desc's own arrays
+// plus the inverse element mass matrices of curved_setup.h.
+#define DGB_EMULATE 1
+#include "cuda_emu.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../dgfem-acoustic_b200/csrc/stage_curved.cu"
+
+using namespace dgb;
+
+namespace {
+thread_local std::string g_err;
+
+CurvedMesh fromDesc(const dgb_desc* d, const std::vector<double>& Minv) {
+    if (d->nGeomEl != d->nG || d->nGeomF != d->nGf) throw std::runtime_error("the desc must carry one Jacobian / normal per integration point");
+    CurvedMesh C{};
+    C.dim = d->dim; C.Np = d->Np; C.Nfp = d->Nfp; C.Nf = d->Nf; C.K = d->K; C.F = d->F; C.nG = d->nG; C.nGf = d->nGf; C.fc = d->fc;
+    C.elBasis = d->elBasisFct; C.elUGrad = d->elUGradBasisFct; C.elWeight = d->elWeight; C.fBasis = d->fBasisFct; C.fWeight = d->fWeight;
+    C.elJac = d->elJacobian; C.elDet = d->elJacobianDet; C.fNormal = d->fNormal; C.fDet = d->fJacobianDet;
+    C.elFId = d->elFId; C.elFOrientation = d->elFOrientation; C.fNbrElId = d->fNbrElId; C.fNToElNId = d->fNToElNId;
+    C.fIsBoundary = d->fIsBoundary; C.fBC = d->fBC; C.Minv = Minv.data();
+    C.c0 = d->c0; C.rho0 = d->rho0; C.v0[0] = d->v0[0]; C.v0[1] = d->v0[1]; C.v0[2] = d->v0[2];
+    C.stride = (int64_t)d->K * d->Np;
+    return C;
+}
+}  // namespace
+
+extern "C" {
+const char* cve_last_error(void) { return g_err.c_str(); }
+
+int cve_is_curved(const dgb_desc* d) { return isCurved(d) ? 1 : 0; }
+
+// integrator 1: nsteps of RK4, 0: forward Euler, 2: rhs = L(u) written over u (MODE_RHS)
+int cve_run(const dgb_desc* d, int integrator, double* u, int nsteps) {
+    try {
+        const std::vector<double> Minv = curvedInverseMass(d);
+        const CurvedMesh C = fromDesc(d, Minv);
+        const size_t n = (size_t)4 * d->K * d->Np;
+        std::vector<double> U(u, u + n), ACC(n, 0.0), YA(n, 0.0), YB(n, 0.0);
+        double *pU = U.data(), *pYA = YA.data(), *pYB = YB.data();
+        StageArgs A{};
+        A.acc = ACC.data(); A.dt = d->dt; A.eBegin = 0; A.eEnd = d->K;
+        if (integrator == 2) {
+            A.yin = pU; A.u = pU; A.yout = pYA; A.mode = MODE_RHS; A.dt = 1.0;
+            launchCurved(C, A, nullptr);
+            std::copy(YA.begin(), YA.end(), u);
+            return 0;
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            A.u = pU;
+            if (integrator == 0) {
+                A.yin = pU; A.yout = pYA; A.mode = MODE_EULER; launchCurved(C, A, nullptr);
+                std::swap(pU, pYA);
+                continue;
+            }
+            A.yin = pU;  A.yout = pYA; A.mode = MODE_RK1; launchCurved(C, A, nullptr);
+            A.yin = pYA; A.yout = pYB; A.mode = MODE_RK2; launchCurved(C, A, nullptr);
+            A.yin = pYB; A.yout = pYA; A.mode = MODE_RK3; launchCurved(C, A, nullptr);
+            A.yin = pYA; A.yout = nullptr; A.mode = MODE_RK4; launchCurved(C, A, nullptr);
+        }
+        std::copy(pU, pU + n, u);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}

@@ -1,0 +1,102 @@
+"""Curved (non-affine) elements, SURVEY.md §8 f3.
+
+CPU: the curved-element CUDA kernel (dgfem-acoustic_b200/csrc/stage_curved.cu, the file itself) runs through the CUDA
+emulation of oracle/cuda_emu.h on warped isoparametric meshes and is compared with the oracle's FAITHFUL mode — the
+reference's own loops, which tests/test_oracle_vs_reference.py pins against the reference binary on such meshes.
+GPU (gated, the kernel was written after the round's GPU budget was spent): the engine itself through the C ABI."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def cve():
+    lib = C.CDLL(str(ROOT / "oracle" / "libcurvedemu.so"))
+    lib.cve_last_error.restype = C.c_char_p
+    lib.cve_run.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+    lib.cve_is_curved.argtypes = [C.c_void_p]
+    return lib
+
+
+def _case(pkg, mesh_dir, name, order, v0, warp):
+    model = pkg.Model.make_cube(int(name.split(":")[1]), -10.0, 10.0, order) if name.startswith("cube:") else pkg.Model.open_msh(mesh_dir / name, order)
+    if warp:
+        model.warp(*warp)
+    mesh = pkg.Mesh(model, pkg.Config())
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=v0, dt=0.05 * mesh.h_min() / (343.0 * (2 * order + 1)))
+    b = np.nonzero(mesh.fIsBoundary)[0]
+    mesh.fBC[b[::2]] = 1
+    rng = np.random.default_rng(2)
+    x = mesh.node_coords
+    u = np.zeros((4, mesh.N))
+    for q in range(4 if mesh.dim == 3 else 3):
+        k, ph = rng.uniform(0.5, 2, 3), rng.uniform(0, 6, 3)
+        u[q] = np.cos(k[0] * x[:, 0] * 0.3 + ph[0]) * np.cos(k[1] * x[:, 1] * 0.3 + ph[1]) * np.cos(k[2] * x[:, 2] * 0.3 + ph[2])
+    u[1:] *= 1e-3
+    return mesh, u
+
+
+CASES = [("square.msh", 2, (8.0, -3.0, 0.0), (0.15, 0.9)), ("cube:3", 2, (8.0, -3.0, 2.0), (0.3, 0.4)), ("cube:2", 4, (0.0, 0.0, 0.0), (0.4, 0.3)),
+         ("cube:2", 3, (1.0, 2.0, 3.0), (0.3, 0.5))]
+
+
+@pytest.mark.parametrize("name,order,v0,warp", CASES)
+def test_emulated_curved_kernel_equals_the_faithful_oracle(pkg, oracle_mod, cve, mesh_dir, name, order, v0, warp):
+    mesh, u = _case(pkg, mesh_dir, name, order, v0, warp)
+    d = C.cast(mesh.desc_p, C.c_void_p)
+    assert cve.cve_is_curved(d) == 1
+    orc = oracle_mod.Oracle(mesh)
+    ref = orc.eval_rhs(oracle_mod.Oracle.FAITHFUL, u)
+    got = u.copy()
+    assert cve.cve_run(d, 2, got.ctypes.data_as(dp), 0) == 0, cve.cve_last_error()
+    for q in range(4):
+        if np.abs(ref[q]).max() > 0:
+            assert rel_l2(got[q], ref[q]) < 1e-12
+        else:
+            assert np.abs(got[q]).max() == 0.0
+    for integrator, ident in ((1, pkg.RUNGE_KUTTA), (0, pkg.EULER1)):
+        got = u.copy()
+        assert cve.cve_run(d, integrator, got.ctypes.data_as(dp), 2) == 0
+        want = u.copy()
+        oracle_mod.Oracle(mesh).run(oracle_mod.Oracle.FAITHFUL, ident, want, 0.0, 2)
+        for q in range(4):
+            if np.abs(want[q]).max() > 0:
+                assert rel_l2(got[q], want[q]) < 1e-12
+
+
+def test_straight_sided_meshes_are_not_flagged(pkg, cve, mesh_dir):
+    mesh, _ = _case(pkg, mesh_dir, "cube:2", 3, (0.0, 0.0, 0.0), None)
+    assert cve.cve_is_curved(C.cast(mesh.desc_p, C.c_void_p)) == 0
+    assert mesh.desc.nGeomEl == 1 and mesh.desc.nGeomF == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("DGB_TEST_CURVED") != "1", reason="curved-element kernel not yet run on hardware: set DGB_TEST_CURVED=1")
+@pytest.mark.parametrize("name,order,v0,warp", CASES + [("disk.msh", 3, (0.0, 0.0, 0.0), (0.05, 1.5))])
+def test_engine_on_curved_meshes(pkg, oracle_mod, mesh_dir, name, order, v0, warp):
+    mesh, u = _case(pkg, mesh_dir, name, order, v0, warp)
+    eng = pkg.Engine(mesh)
+    assert eng.kernel_name == "stage_curved"
+    orc = oracle_mod.Oracle(mesh)
+    rhs = eng.eval_rhs(u)
+    ref = orc.eval_rhs(oracle_mod.Oracle.FAITHFUL, u)
+    for q in range(4):
+        if np.abs(ref[q]).max() > 0:
+            assert rel_l2(rhs[q], ref[q]) < 1e-10
+    eng.set_state(u)
+    eng.run(pkg.RUNGE_KUTTA, 0.0, 6)
+    got = eng.get_state()
+    want = u.copy()
+    orc.run(oracle_mod.Oracle.FAITHFUL, pkg.RUNGE_KUTTA, want, 0.0, 6)
+    for q in range(4):
+        if np.abs(want[q]).max() > 0:
+            assert rel_l2(got[q], want[q]) < 1e-10
+    with pytest.raises(pkg.DgbError):
+        eng.set_option("kernel", 3)
+    eng.close()
