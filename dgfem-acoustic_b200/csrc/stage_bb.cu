@@ -21,14 +21,8 @@
 #include "bb_ops.h"
 
 // The CPU tests run THIS file through a small CUDA emulation (oracle/cuda_emu.h, oracle/bb_emulate.cpp: one OS thread per
-// CUDA thread, a barrier for __syncthreads); the few constructs a host compiler cannot take go through these macros.
-#ifdef DGB_EMULATE
-#define DGB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cuemu::dynamicSmem())
-#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) cuemu::launch(kernel, grid, block, smemBytes, __VA_ARGS__)
-#else
-#define DGB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
-#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) kernel<<<grid, block, smemBytes, stream>>>(__VA_ARGS__)
-#endif
+// CUDA thread, a barrier for __syncthreads); the few constructs a host compiler cannot take go through dgb_launch.h.
+#include "dgb_launch.h"
 
 namespace dgb {
 

@@ -15,13 +15,7 @@
 #include "dgb_internal.h"
 #include "dgb_device.cuh"
 
-#ifdef DGB_EMULATE
-#define DGB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cuemu::dynamicSmem())
-#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) cuemu::launch(kernel, grid, block, smemBytes, __VA_ARGS__)
-#else
-#define DGB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
-#define DGB_LAUNCH(kernel, grid, block, smemBytes, stream, ...) kernel<<<grid, block, smemBytes, stream>>>(__VA_ARGS__)
-#endif
+#include "dgb_launch.h"
 
 namespace dgb {
 
