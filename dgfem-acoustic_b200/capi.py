@@ -80,6 +80,7 @@ def load_front():
     lib.dgf_make_cube.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
     lib.dgf_model_free.argtypes = [C.c_void_p]
     lib.dgf_warp_model.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.dgf_warp_model_local.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.dgf_write_msh.argtypes = [C.c_void_p, C.c_char_p]
     lib.dgf_model_dimension.argtypes = [C.c_void_p]
     lib.dgf_parse_config.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(DgfConfig)]
@@ -181,6 +182,11 @@ class Model:
     def warp(self, amp, k):
         """Curved stand-in geometry: every node moves by a smooth field (dgf_warp_model)."""
         load_front().dgf_warp_model(self.h, float(amp), float(k))
+        return self
+
+    def warp_local(self, amp, k, center, radius):
+        """A curved patch inside the ball (center, radius) of an otherwise straight-sided mesh (dgf_warp_model_local)."""
+        load_front().dgf_warp_model_local(self.h, float(amp), float(k), float(center[0]), float(center[1]), float(center[2]), float(radius))
         return self
 
     @property

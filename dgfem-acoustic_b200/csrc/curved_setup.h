@@ -23,7 +23,8 @@ struct CurvedMesh {
     const int32_t *elFId, *elFOrientation, *fNbrElId, *fNToElNId;   // [K][Nf], [K][Nf], [F][2], [F][Nfp][2]
     const uint8_t* fIsBoundary;                                     // [F]
     const int32_t* fBC;                                             // [F]
-    const double* Minv;                                             // [K][Np][Np] inverse element mass matrices
+    const double* Minv;                                             // [K - firstCurved][Np][Np] inverse element mass matrices
+    int firstCurved;                                                // elements >= firstCurved take this path (0: all of them)
     double c0, rho0, v0[3];
     int64_t stride;                                                 // K*Np
 };
@@ -45,13 +46,47 @@ inline bool isCurved(const dgb_desc* d) {
     return false;
 }
 
-// inverse element mass matrices, M_ij = sum_g phi_i(g) phi_j(g) w_g detJ(el, g)   (Mesh.cpp:440-466), extended precision
-inline std::vector<double> curvedInverseMass(const dgb_desc* d) {
+// per element: does its Jacobian vary over its integration points, or the normal / surface Jacobian over one of its faces?
+inline std::vector<uint8_t> curvedElements(const dgb_desc* d) {
+    std::vector<uint8_t> flag(d->K, 0), fflag(d->F, 0);
+    if (d->nGeomF > 1)
+        for (int f = 0; f < d->F; ++f)
+            for (int g = 1; g < d->nGf && !fflag[f]; ++g) {
+                for (int k = 0; k < 3; ++k)
+                    if (std::fabs(d->fNormal[((size_t)f * d->nGf) * 3 + k] - d->fNormal[((size_t)f * d->nGf + g) * 3 + k]) > 1e-11) fflag[f] = 1;
+                const double a = d->fJacobianDet[(size_t)f * d->nGf], b = d->fJacobianDet[(size_t)f * d->nGf + g];
+                if (std::fabs(a - b) > 1e-11 * (std::fabs(a) + std::fabs(b))) fflag[f] = 1;
+            }
+    for (int el = 0; el < d->K; ++el) {
+        if (d->nGeomEl > 1)
+            for (int g = 1; g < d->nG && !flag[el]; ++g)
+                for (int k = 0; k < 9; ++k) {
+                    const double a = d->elJacobian[((size_t)el * d->nG) * 9 + k], b = d->elJacobian[((size_t)el * d->nG + g) * 9 + k];
+                    if (std::fabs(a - b) > 1e-11 * (std::fabs(a) + std::fabs(b) + 1e-300) + 1e-13) flag[el] = 1;
+                }
+        for (int lf = 0; lf < d->Nf; ++lf) if (fflag[d->elFId[(size_t)el * d->Nf + lf]]) flag[el] = 1;
+    }
+    return flag;
+}
+
+// Straight-sided elements may keep the collapsed kernels if the curved ones form a suffix of the numbering (the front end of
+// this repository orders them so): returns the first curved element of that suffix, or 0 (everything through the curved
+// kernel) when curved and straight-sided elements interleave.
+inline int curvedSuffixStart(const std::vector<uint8_t>& flag) {
+    int first = (int)flag.size();
+    while (first > 0 && flag[first - 1]) --first;
+    for (int el = 0; el < first; ++el) if (flag[el]) return 0;
+    return first;
+}
+
+// inverse element mass matrices of the elements >= first, M_ij = sum_g phi_i(g) phi_j(g) w_g detJ(el, g)  (Mesh.cpp:440-466),
+// extended precision
+inline std::vector<double> curvedInverseMass(const dgb_desc* d, int first = 0) {
     const int Np = d->Np, nG = d->nG, K = d->K;
     if (d->nGeomEl != nG) throw std::runtime_error("curved elements need one Jacobian per integration point (nGeomEl == nG)");
-    std::vector<double> out((size_t)K * Np * Np);
+    std::vector<double> out((size_t)(K - first) * Np * Np);
 #pragma omp parallel for schedule(static)
-    for (int el = 0; el < K; ++el) {
+    for (int el = first; el < K; ++el) {
         std::vector<long double> A((size_t)Np * Np, 0), B((size_t)Np * Np, 0);
         for (int g = 0; g < nG; ++g) {
             const long double wd = (long double)d->elWeight[g] * d->elJacobianDet[(size_t)el * nG + g];
@@ -75,7 +110,7 @@ inline std::vector<double> curvedInverseMass(const dgb_desc* d) {
                 for (int k = 0; k < Np; ++k) { A[(size_t)r * Np + k] -= f * A[(size_t)c * Np + k]; B[(size_t)r * Np + k] -= f * B[(size_t)c * Np + k]; }
             }
         }
-        for (size_t i = 0; i < (size_t)Np * Np; ++i) out[(size_t)el * Np * Np + i] = (double)B[i];
+        for (size_t i = 0; i < (size_t)Np * Np; ++i) out[(size_t)(el - first) * Np * Np + i] = (double)B[i];
     }
     return out;
 }

@@ -140,6 +140,8 @@ struct dgb_handle {
     // curved (non-affine) meshes: the reference's own tables on the device + inverse element mass matrices; every
     // element then goes through stage_curved.cu
     bool curved = false;
+    int firstCurved = 0;             // elements [0, firstCurved) are straight-sided and keep the collapsed kernels
+    std::string curvedName;          // kernel name reported for a curved handle
     CurvedMesh CM{};
     std::vector<void*> curvedAllocs;
     double *dV = nullptr, *dVinv = nullptr;
@@ -325,7 +327,8 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         throw DgbException(DGB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
-    const bool curved = isCurved(d);
+    const std::vector<uint8_t> elCurved = curvedElements(d);
+    const bool curved = std::find(elCurved.begin(), elCurved.end(), (uint8_t)1) != elCurved.end();
     if (curved && nranks > 1) throw DgbException(DGB_ERR_UNSUPPORTED, "curved (non-affine) elements are not supported on partitioned handles yet");
     if (curved && (d->nGeomEl != d->nG || d->nGeomF != d->nGf))
         throw DgbException(DGB_ERR_ARG, "curved elements need one Jacobian / normal per integration point (nGeomEl == nG, nGeomF == nGf)");
@@ -484,13 +487,14 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
             C.elFId = up(d->elFId, (size_t)K * Nf); C.elFOrientation = up(d->elFOrientation, (size_t)K * Nf);
             C.fNbrElId = up(d->fNbrElId, F * 2); C.fNToElNId = up(d->fNToElNId, F * Nfp * 2);
             C.fIsBoundary = up(d->fIsBoundary, F); C.fBC = up(d->fBC, F);
-            const std::vector<double> Minv = curvedInverseMass(d);
+            // straight-sided elements keep the collapsed kernels when the curved ones form a suffix of the numbering
+            h->firstCurved = curvedSuffixStart(elCurved);
+            const std::vector<double> Minv = curvedInverseMass(d, h->firstCurved);
             C.Minv = up(Minv.data(), Minv.size());
+            C.firstCurved = h->firstCurved;
             C.c0 = d->c0; C.rho0 = d->rho0; C.v0[0] = d->v0[0]; C.v0[1] = d->v0[1]; C.v0[2] = d->v0[2];
             C.stride = M.stride;
-            h->ws = h->tiled = StageKernel{};
-            h->active = h->generic;  // placeholder entry (launchStage dispatches on h->curved)
-            h->active.name = "stage_curved";
+            h->curvedName = h->firstCurved > 0 ? std::string(h->active.name) + " + stage_curved" : std::string("stage_curved");
         }
         // Bernstein-Bezier path (opt-in): conversion matrices, permutation tables, self-check of the closed-form lift
         h->bbKernel = curved ? StageKernel{} : selectBBKernel(dim, d->order);
@@ -552,10 +556,18 @@ void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     A.smReserve = (h->partitioned && h->exchangeMode == 0 && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches beside NCCL kernels only
     const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
     if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
-    if (h->curved) launchCurved(h->CM, A, h->stream);
-    else h->active.launch(h->M, A, h->stream);
+    int nLaunched = 1;
+    if (h->curved) {  // straight-sided prefix through the collapsed kernel, curved suffix through the reference's quadrature loops
+        nLaunched = 0;
+        StageArgs B = A;
+        B.eEnd = std::min(eEnd, h->firstCurved);
+        if (B.eEnd > B.eBegin) { h->active.launch(h->M, B, h->stream); ++nLaunched; }
+        B = A;
+        B.eBegin = std::max(eBegin, h->firstCurved);
+        if (B.eEnd > B.eBegin) { launchCurved(h->CM, B, h->stream); ++nLaunched; }
+    } else h->active.launch(h->M, A, h->stream);
     if (t) { cudaEventRecord(h->stageEv[h->stageEvUsed + 1], h->stream); h->stageEvUsed += 2; }
-    ++h->launches;
+    h->launches += nLaunched;
 }
 
 // Halo exchange of array y (owned border elements -> the peers' halo slots), SURVEY §8 e1.
@@ -1225,17 +1237,15 @@ int dgb_synchronize(dgb_handle* h) {
 double dgb_last_run_ms(dgb_handle* h) { return h ? h->lastRunMs : 0.0; }
 double dgb_last_stage_kernel_ms(dgb_handle* h) { return h ? h->lastStageMs : 0.0; }
 int64_t dgb_launch_count(dgb_handle* h) { return h ? h->launches : 0; }
-const char* dgb_kernel_name(dgb_handle* h) { return h ? h->active.name : "none"; }
+const char* dgb_kernel_name(dgb_handle* h) { return !h ? "none" : h->curved ? h->curvedName.c_str() : h->active.name; }
 
 int dgb_set_option(dgb_handle* h, const char* key, int value) {
     return guarded([&] {
         if (!h || !key) throw DgbException(DGB_ERR_ARG, "null argument");
         const std::string k(key);
         if (k == "kernel") {
-            if (h->curved) {
-                if (value != 0) throw DgbException(DGB_ERR_UNSUPPORTED, "curved meshes run the curved-element kernel only");
-                return;
-            }
+            if (h->curved && (h->firstCurved == 0 ? value != 0 : value > 3))
+                throw DgbException(DGB_ERR_UNSUPPORTED, "curved meshes: the curved elements run the curved-element kernel, the straight-sided ones kernels 0..3");
             if (value == 1) h->active = h->generic;
             else if (value == 2) {
                 if (!h->tiled.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no tiled kernel for this dim/order");
@@ -1248,6 +1258,7 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
                 h->active = value == 4 ? h->bbKernel : h->bbSeqKernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes
+            if (h->curved) h->curvedName = h->firstCurved > 0 ? std::string(h->active.name) + " + stage_curved" : std::string("stage_curved");
             const bool wantBB = h->active.launch && (h->active.launch == h->bbKernel.launch || h->active.launch == h->bbSeqKernel.launch);
             if (wantBB != h->bbMode) {
                 finishExchange(h);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(CURVED_THREADS) stageCurvedKernel(CurvedMesh C
     }
 
     // k = dt * M_el^-1 (S - F) (the row-major inverse read column-major like the reference's Eigen::Map), fused RK update
-    const double* Mi = C.Minv + (int64_t)el * Np * Np;
+    const double* Mi = C.Minv + (int64_t)(el - C.firstCurved) * Np * Np;
     for (int i = tid; i < 4 * Np; i += CURVED_THREADS) {
         const int q = i / Np, n = i - q * Np;
         double s = 0.0;

@@ -110,6 +110,12 @@ extern "C" int dgf_warp_model(dgf_model* m, double amp, double k) {
     gml::warp(m->m, amp, k);
     return 0;
 }
+extern "C" int dgf_warp_model_local(dgf_model* m, double amp, double k, double cx, double cy, double cz, double radius) {
+    if (!m || !(radius > 0)) return -1;
+    const double c[3] = {cx, cy, cz};
+    gml::warpLocal(m->m, amp, k, c, radius);
+    return 0;
+}
 extern "C" int dgf_model_dimension(const dgf_model* m) { return m ? m->m.dimension() : -1; }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,6 +306,39 @@ extern "C" dgf_mesh* dgf_mesh_build(dgf_model* model, const dgf_config* cfg) {
             M->elNodeTags.assign(nodes.begin(), nodes.end());
         }
         const int K = (int)M->elTags.size();
+        if (gm.curved) {
+            // a curved model: straight-sided elements first, curved ones last (stable), so that the engine can run its collapsed
+            // kernels on a prefix and the curved-element kernel on the suffix. An element is straight-sided if every node sits
+            // where the affine map of its vertices puts it. (A fully warped model keeps its order: all elements are curved.)
+            const gml::RefElement& lin = gml::refElement(dim, 1);
+            std::vector<double> phi(lin.np);
+            std::vector<int> straight, bent;
+            for (int el = 0; el < K; ++el) {
+                const int* nt = &M->elNodeTags[(size_t)el * Np];
+                double scale = 0, dev = 0;
+                for (int v = 1; v < lin.np; ++v)
+                    for (int x = 0; x < 3; ++x) scale = std::max(scale, std::fabs(gm.node(nt[v])[x] - gm.node(nt[0])[x]));
+                for (int n = lin.np; n < Np; ++n) {
+                    lin.basis(&re.uvw[3 * n], phi.data());
+                    for (int x = 0; x < 3; ++x) {
+                        double sx = 0;
+                        for (int v = 0; v < lin.np; ++v) sx += phi[v] * gm.node(nt[v])[x];
+                        dev = std::max(dev, std::fabs(sx - gm.node(nt[n])[x]));
+                    }
+                }
+                (dev > 1e-12 * scale ? bent : straight).push_back(el);
+            }
+            if (!bent.empty() && !straight.empty()) {
+                std::vector<int32_t> tags2, nodes2;
+                straight.insert(straight.end(), bent.begin(), bent.end());
+                for (int el : straight) {
+                    tags2.push_back(M->elTags[el]);
+                    nodes2.insert(nodes2.end(), M->elNodeTags.begin() + (size_t)el * Np, M->elNodeTags.begin() + (size_t)(el + 1) * Np);
+                }
+                M->elTags.swap(tags2);
+                M->elNodeTags.swap(nodes2);
+            }
+        }
         const gml::Quadrature& q = gml::gaussRule(dim, 2 * order);  // "Gauss" + 2*order (Mesh.cpp:31)
         const int nG = q.n;
         M->elBasisFct.resize((size_t)nG * Np);

@@ -800,16 +800,24 @@ void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const 
     completeJacobian(dim, jac, det);
 }
 
-void warp(Model& m, double amp, double k) {
+static void warpImpl(Model& m, double amp, double k, const double* center, double radius) {
     const int dim = m.dimension();
     for (int tag = 0; tag <= m.maxNodeTag; ++tag) {
         double* x = &m.xyz[3 * (size_t)tag];
         const double x0 = x[0], x1 = x[1], x2 = x[2];
-        x[0] = x0 + amp * std::sin(k * x1 + 0.3) * (dim >= 2 ? 1.0 : 0.0) + (dim == 3 ? 0.5 * amp * std::sin(k * x2 + 0.2) : 0.0);
-        if (dim >= 2) x[1] = x1 + amp * std::sin(k * (dim == 3 ? x2 : x0) + 0.7);
-        if (dim == 3) x[2] = x2 + amp * std::sin(k * x0 + 1.1);
+        double w = 1.0;
+        if (center) {
+            const double r2 = ((x0 - center[0]) * (x0 - center[0]) + (x1 - center[1]) * (x1 - center[1]) + (x2 - center[2]) * (x2 - center[2])) / (radius * radius);
+            w = r2 < 1.0 ? (1.0 - r2) * (1.0 - r2) : 0.0;
+        }
+        if (w == 0.0) continue;
+        x[0] = x0 + w * (amp * std::sin(k * x1 + 0.3) * (dim >= 2 ? 1.0 : 0.0) + (dim == 3 ? 0.5 * amp * std::sin(k * x2 + 0.2) : 0.0));
+        if (dim >= 2) x[1] = x1 + w * amp * std::sin(k * (dim == 3 ? x2 : x0) + 0.7);
+        if (dim == 3) x[2] = x2 + w * amp * std::sin(k * x0 + 1.1);
     }
     m.curved = true;
 }
+void warp(Model& m, double amp, double k) { warpImpl(m, amp, k, nullptr, 0.0); }
+void warpLocal(Model& m, double amp, double k, const double center[3], double radius) { warpImpl(m, amp, k, center, radius); }
 
 }  // namespace gml

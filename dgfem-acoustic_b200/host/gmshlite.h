@@ -105,5 +105,8 @@ void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const 
 // dimension (2D models stay in their plane): turns a straight-sided order-p mesh into a conforming curved isoparametric one
 // (the stand-in for meshing a curved geometry with `gmsh -order p`). Sets Model::curved.
 void warp(Model& m, double amp, double k);
+// The same displacement multiplied by the window (1 - (r/R)^2)^2 around `center` (zero for r >= R): only the elements that
+// reach into the ball become curved, the rest of the mesh stays exactly straight-sided (a curved layer in a straight mesh).
+void warpLocal(Model& m, double amp, double k, const double center[3], double radius);
 
 }  // namespace gml

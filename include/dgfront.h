@@ -56,6 +56,10 @@ int dgf_write_msh(const dgf_model* m, const char* path);
  * turns the straight-sided order-p model into a conforming curved isoparametric one (what `gmsh -order p` produces along
  * curved boundaries). dgf_mesh_build then stores one Jacobian / normal per integration point (nGeomEl = nG, nGeomF = nGf). */
 int dgf_warp_model(dgf_model* m, double amp, double k);
+/* The same inside a ball only (window (1-(r/R)^2)^2): a curved patch in an otherwise straight-sided mesh. dgf_mesh_build then
+ * numbers the straight-sided elements first and the curved ones last (the engine runs its collapsed kernels on the first
+ * group and the curved-element kernel on the second). */
+int dgf_warp_model_local(dgf_model* m, double amp, double k, double cx, double cy, double cz, double radius);
 void dgf_model_free(dgf_model* m);
 int dgf_model_dimension(const dgf_model* m);
 

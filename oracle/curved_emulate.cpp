@@ -16,14 +16,14 @@ using namespace dgb;
 namespace {
 thread_local std::string g_err;
 
-CurvedMesh fromDesc(const dgb_desc* d, const std::vector<double>& Minv) {
+CurvedMesh fromDesc(const dgb_desc* d, const std::vector<double>& Minv, int first) {
     if (d->nGeomEl != d->nG || d->nGeomF != d->nGf) throw std::runtime_error("the desc must carry one Jacobian / normal per integration point");
     CurvedMesh C{};
     C.dim = d->dim; C.Np = d->Np; C.Nfp = d->Nfp; C.Nf = d->Nf; C.K = d->K; C.F = d->F; C.nG = d->nG; C.nGf = d->nGf; C.fc = d->fc;
     C.elBasis = d->elBasisFct; C.elUGrad = d->elUGradBasisFct; C.elWeight = d->elWeight; C.fBasis = d->fBasisFct; C.fWeight = d->fWeight;
     C.elJac = d->elJacobian; C.elDet = d->elJacobianDet; C.fNormal = d->fNormal; C.fDet = d->fJacobianDet;
     C.elFId = d->elFId; C.elFOrientation = d->elFOrientation; C.fNbrElId = d->fNbrElId; C.fNToElNId = d->fNToElNId;
-    C.fIsBoundary = d->fIsBoundary; C.fBC = d->fBC; C.Minv = Minv.data();
+    C.fIsBoundary = d->fIsBoundary; C.fBC = d->fBC; C.Minv = Minv.data(); C.firstCurved = first;
     C.c0 = d->c0; C.rho0 = d->rho0; C.v0[0] = d->v0[0]; C.v0[1] = d->v0[1]; C.v0[2] = d->v0[2];
     C.stride = (int64_t)d->K * d->Np;
     return C;
@@ -35,11 +35,37 @@ const char* cve_last_error(void) { return g_err.c_str(); }
 
 int cve_is_curved(const dgb_desc* d) { return isCurved(d) ? 1 : 0; }
 
+// first element of the curved suffix (dgb_create's decision): K if nothing is curved, 0 if everything goes through the curved kernel
+int cve_first_curved(const dgb_desc* d) {
+    const std::vector<uint8_t> flag = curvedElements(d);
+    bool any = false;
+    for (uint8_t f : flag) any = any || f;
+    return any ? curvedSuffixStart(flag) : d->K;
+}
+
+// rhs = L(u) of the elements >= first only (the others keep u's values): the curved half of a mixed handle
+int cve_rhs_suffix(const dgb_desc* d, int first, double* u) {
+    try {
+        const std::vector<double> Minv = curvedInverseMass(d, first);
+        const CurvedMesh C = fromDesc(d, Minv, first);
+        const size_t n = (size_t)4 * d->K * d->Np;
+        std::vector<double> U(u, u + n), ACC(n, 0.0), Y(u, u + n);
+        StageArgs A{};
+        A.yin = U.data(); A.u = U.data(); A.acc = ACC.data(); A.yout = Y.data(); A.mode = MODE_RHS; A.dt = 1.0; A.eBegin = first; A.eEnd = d->K;
+        launchCurved(C, A, nullptr);
+        std::copy(Y.begin(), Y.end(), u);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 // integrator 1: nsteps of RK4, 0: forward Euler, 2: rhs = L(u) written over u (MODE_RHS)
 int cve_run(const dgb_desc* d, int integrator, double* u, int nsteps) {
     try {
         const std::vector<double> Minv = curvedInverseMass(d);
-        const CurvedMesh C = fromDesc(d, Minv);
+        const CurvedMesh C = fromDesc(d, Minv, 0);
         const size_t n = (size_t)4 * d->K * d->Np;
         std::vector<double> U(u, u + n), ACC(n, 0.0), YA(n, 0.0), YB(n, 0.0);
         double *pU = U.data(), *pYA = YA.data(), *pYB = YB.data();

@@ -37,8 +37,10 @@ void open(const std::string& fileName) {
     g_model = gml::readMsh(fileName);
     if (const char* o = std::getenv("GMSHLITE_ORDER")) gml::elevate(g_model, std::atoi(o));
     if (const char* w = std::getenv("GMSHLITE_WARP")) {  // "amp,k": the curved stand-in geometry (gml::warp), same as dgf_warp_model
-        double amp = 0, k = 0;
-        if (std::sscanf(w, "%lf,%lf", &amp, &k) == 2) gml::warp(g_model, amp, k);
+        double amp = 0, k = 0, c[3] = {0, 0, 0}, R = 0;
+        const int got = std::sscanf(w, "%lf,%lf,%lf,%lf,%lf,%lf", &amp, &k, &c[0], &c[1], &c[2], &R);
+        if (got == 6) gml::warpLocal(g_model, amp, k, c, R);  // "amp,k,cx,cy,cz,R": a curved patch in a straight-sided mesh
+        else if (got >= 2) gml::warp(g_model, amp, k);
     }
 }
 namespace option { void setNumber(const std::string&, const double) {} }
