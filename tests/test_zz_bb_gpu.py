@@ -2,7 +2,7 @@
 
 The operator code of this kernel is checked on the CPU (tests/test_bb_ops.py runs the same templates on the host); the
 kernel around it was written after this round's GPU budget was spent and has not run on hardware yet, so the file is
-gated: DGB_TEST_BB=1 enables it (first thing to run next round, profiles/run_bb.sh). Tolerance 1e-10 as everywhere."""
+gated: DGB_TEST_BB=1 enables it (first thing to run next round, profiles/run_unverified.sh). Tolerance 1e-10 as everywhere."""
 import os
 
 import numpy as np
