@@ -9,6 +9,7 @@
 mkdir -p gpurun_out
 DGB_TEST_BB=1 timeout 900 python -m pytest tests/test_zz_bb_gpu.py -x -q 2>&1 | tee gpurun_out/bb_tests.log | tail -15
 DGB_TEST_CURVED=1 timeout 900 python -m pytest tests/test_curved.py -x -q -m gpu 2>&1 | tee gpurun_out/curved_tests.log | tail -15
+DGB_TEST_CLI=1 timeout 600 python -m pytest tests/test_zz_cli_gpu.py -x -q 2>&1 | tee gpurun_out/cli_tests.log | tail -8
 for K in 4 5 3; do
   name=$([ $K = 4 ] && echo bb || ([ $K = 5 ] && echo bbseq || echo ws))
   timeout 900 python bench.py --no-cpu-baseline --kernel $K > gpurun_out/${name}_bench.json 2> gpurun_out/${name}_bench.err
