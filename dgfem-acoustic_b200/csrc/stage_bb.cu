@@ -68,7 +68,8 @@ __device__ __forceinline__ void cpAsync8(double* smemDst, const double* gmemSrc)
     *smemDst = *gmemSrc;
 #else
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmemSrc) : "memory");
+    const size_t src = __cvta_generic_to_global(gmemSrc);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 #endif
 }
 __device__ __forceinline__ void cpAsyncCommit() {
