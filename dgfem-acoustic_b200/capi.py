@@ -350,6 +350,11 @@ def load_dgb():
     lib.dgb_get_probes.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int)]
     lib.dgb_set_receivers.argtypes = [C.c_void_p, C.c_int, c_int32_p, c_double_p]
     lib.dgb_get_receivers.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int)]
+    lib.dgb_snapshot_begin.argtypes = [C.c_void_p, c_double_p]
+    lib.dgb_snapshot_end.argtypes = [C.c_void_p]
+    lib.dgb_host_alloc.restype = C.c_void_p
+    lib.dgb_host_alloc.argtypes = [C.c_uint64]
+    lib.dgb_host_free.argtypes = [C.c_void_p]
     lib.dgb_run.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, c_double_p]
     lib.dgb_eval_rhs.argtypes = [C.c_void_p, c_double_p, c_double_p]
     lib.dgb_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -404,6 +409,14 @@ class Engine:
         u = out if out is not None else np.zeros((4, self.N), dtype=np.float64)
         self._check(self.lib.dgb_get_state(self.h, _as(c_double_p, u)))
         return u
+
+    def snapshot_begin(self, out):
+        """Asynchronous get_state into `out` (ideally pinned memory); snapshot_end() waits for it."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == 4 * self.N
+        self._check(self.lib.dgb_snapshot_begin(self.h, _as(c_double_p, out)))
+
+    def snapshot_end(self):
+        self._check(self.lib.dgb_snapshot_end(self.h))
 
     def set_sources(self, offsets, idx, amp, freq, phase, duration):
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)

@@ -183,6 +183,11 @@ struct dgb_handle {
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int32_t* dSendElems = nullptr;
     double* hostStage = nullptr;  // pinned, [4][stride], partitioned handles only
+    // asynchronous snapshot: device-side copy of the state + a copy stream
+    double* dSnap = nullptr;
+    cudaStream_t snapStream = nullptr;
+    cudaEvent_t evSnapReady = nullptr, evSnapDone = nullptr;
+    bool snapPending = false;
     // direct peer-to-peer halo exchange (dgb_set_option("exchange", 1), halo_p2p.cu): U / YA / YB and the epoch flags live in
     // ONE allocation ("arena") that every peer maps through CUDA IPC
     int exchangeMode = 0;            // 0: ncclSend/ncclRecv, 1: stores into the peers' halo slots + epoch flags
@@ -208,6 +213,9 @@ void freeHandle(dgb_handle* h) {
     if (h->comm) nccl().CommDestroy(h->comm);
     if (h->stepGraph) cudaGraphExecDestroy(h->stepGraph);
     if (h->hostStage) cudaFreeHost(h->hostStage);
+    if (h->snapStream) { cudaStreamSynchronize(h->snapStream); cudaStreamDestroy(h->snapStream); }
+    for (auto e : {h->evSnapReady, h->evSnapDone}) if (e) cudaEventDestroy(e);
+    F(h->dSnap);
     for (auto& pm : h->peerMap) if (pm.opened) cudaIpcCloseMemHandle(pm.opened);
     if (h->arena && h->comm && h->stream) {
         // peers still map this rank's arena: every rank closes its mappings (above) before anybody frees (collective destroy)
@@ -1070,6 +1078,45 @@ int dgb_get_state(dgb_handle* h, double* u) {
         stateToHost(h, h->U, u);
     });
 }
+
+int dgb_snapshot_begin(dgb_handle* h, double* u_host) {
+    return guarded([&] {
+        if (!h || !u_host) throw DgbException(DGB_ERR_ARG, "null argument");
+        if (!h->stateSet) throw DgbException(DGB_ERR_STATE, "dgb_snapshot_begin before dgb_set_state");
+        if (h->partitioned) throw DgbException(DGB_ERR_UNSUPPORTED, "asynchronous snapshots are not available on partitioned handles");
+        const size_t n = (size_t)4 * h->M.stride;
+        if (!h->dSnap) {
+            h->dSnap = devAlloc<double>(n);
+            CUDA_CHECK(cudaStreamCreateWithFlags(&h->snapStream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&h->evSnapReady, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&h->evSnapDone, cudaEventDisableTiming));
+        }
+        if (h->snapPending) CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evSnapDone, 0));  // the previous copy still reads the buffer
+        if (h->bbMode) { launchElementMatrix(h->U, h->dSnap, h->M.stride, h->Np, h->M.Kown, h->dV, h->stream); ++h->launches; }  // Bernstein -> nodal
+        else CUDA_CHECK(cudaMemcpyAsync(h->dSnap, h->U, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_CHECK(cudaEventRecord(h->evSnapReady, h->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(h->snapStream, h->evSnapReady, 0));
+        CUDA_CHECK(cudaMemcpyAsync(u_host, h->dSnap, n * sizeof(double), cudaMemcpyDeviceToHost, h->snapStream));
+        CUDA_CHECK(cudaEventRecord(h->evSnapDone, h->snapStream));
+        h->snapPending = true;
+    });
+}
+
+int dgb_snapshot_end(dgb_handle* h) {
+    return guarded([&] {
+        if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
+        if (!h->snapPending) throw DgbException(DGB_ERR_STATE, "dgb_snapshot_end without dgb_snapshot_begin");
+        CUDA_CHECK(cudaEventSynchronize(h->evSnapDone));
+        h->snapPending = false;
+    });
+}
+
+void* dgb_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void dgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32_t* nodeIdx, const double* amp, const double* freq,
                     const double* phase, const double* duration) {

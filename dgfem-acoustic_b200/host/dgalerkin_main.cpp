@@ -76,28 +76,45 @@ int main(int argc, char** argv) {
 
     std::vector<int32_t> snapStep;
     std::vector<double> snapTime, snapU;
+    // snapshots leave the GPU asynchronously (dgb_snapshot_begin / _end, two pinned buffers): the copy of snapshot k overlaps the
+    // steps up to snapshot k+1. If that is not available (partitioned handle, no pinned memory) the plain dgb_get_state is used.
+    double* pinned[2] = {static_cast<double*>(dgb_host_alloc(4 * N * sizeof(double))), static_cast<double*>(dgb_host_alloc(4 * N * sizeof(double)))};
+    bool async = pinned[0] && pinned[1];
+    int inflight = -1;
+    auto collect = [&]() {  // the snapshot in flight has landed: append it
+        if (inflight < 0) return true;
+        if (dgb_snapshot_end(h) != DGB_OK) return false;
+        snapU.insert(snapU.end(), pinned[inflight], pinned[inflight] + 4 * N);
+        inflight = -1;
+        return true;
+    };
     const auto start = std::chrono::system_clock::now();
     int pending = 0;
     double tPending = cfg.timeStart, step = 0, tDisplay = 0;
     for (double t = cfg.timeStart; t <= cfg.timeEnd; t += cfg.timeStep, tDisplay += cfg.timeStep, ++step) {  // solver.cpp:216-217
         if (tDisplay >= cfg.timeRate || step == 0) {
             tDisplay = 0;
-            if (dgb_run(h, integrator, tPending, pending, nullptr) != DGB_OK || dgb_get_state(h, u.data()) != DGB_OK) {
-                std::fprintf(stderr, "Error   : %s\n", dgb_last_error());
-                return EXIT_FAILURE;
+            if (dgb_run(h, integrator, tPending, pending, nullptr) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
+            const int buf = (int)(snapStep.size() & 1);
+            const bool ok = collect();  // the previous snapshot had the whole chunk to reach the host
+            if (ok && async && dgb_snapshot_begin(h, pinned[buf]) == DGB_OK) inflight = buf;
+            else {
+                async = false;
+                if (!ok || dgb_get_state(h, u.data()) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
+                snapU.insert(snapU.end(), u.begin(), u.end());
             }
             drainReceivers(pending);
             pending = 0;
             tPending = t;
             snapStep.push_back((int32_t)step);
             snapTime.push_back(t);
-            snapU.insert(snapU.end(), u.begin(), u.end());
             const auto el = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now() - start);
             std::printf("Info    : [%f/%fs] Step number : %d, Elapsed time: %llds\n", t, cfg.timeEnd, (int)step, (long long)el.count());
         }
         ++pending;
     }
     dgb_run(h, integrator, tPending, pending, nullptr);
+    if (!collect()) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
     drainReceivers(pending);
     if (cfg.nReceivers > 0) {
         const int nrec = (int)(rcvRec.size() / ((size_t)cfg.nReceivers * 4));
@@ -108,6 +125,8 @@ int main(int argc, char** argv) {
     std::printf("Info    : %lld kernel launches, last chunk %.3f ms on the device\n", (long long)dgb_launch_count(h), dgb_last_run_ms(h));
     dgf_write_views(cfg.saveFile, model, mesh, &cfg, (int)snapStep.size(), snapStep.data(), snapTime.data(), snapU.data());
     dgb_destroy(h);
+    dgb_host_free(pinned[0]);
+    dgb_host_free(pinned[1]);
     dgf_mesh_free(mesh);
     dgf_model_free(model);
     return EXIT_SUCCESS;

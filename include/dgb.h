@@ -104,6 +104,17 @@ void dgb_destroy(dgb_handle* h);
 int dgb_set_state(dgb_handle* h, const double* u /* [4][K*Np] */);
 int dgb_get_state(dgb_handle* h, double* u /* [4][K*Np] */);
 
+/* Asynchronous snapshot (the reference copies the state into its Gmsh views at every timeRate, src/solver.cpp:222-238; SURVEY.md
+ * §8 f2: "so that snapshots do not stall the GPU"). dgb_snapshot_begin copies the state into a device-side snapshot buffer on
+ * the compute stream — the next dgb_run may start at once — and starts the device->host copy into u_host on a second stream;
+ * dgb_snapshot_end waits for that copy, after which u_host holds what dgb_get_state would have returned at the time of
+ * dgb_snapshot_begin. One snapshot in flight per handle (a second begin waits for the first copy); u_host should be pinned
+ * (dgb_host_alloc) for the copy to overlap the computation. Single-GPU handles; partitioned ones return DGB_ERR_UNSUPPORTED. */
+int dgb_snapshot_begin(dgb_handle* h, double* u_host /* [4][K*Np] */);
+int dgb_snapshot_end(dgb_handle* h);
+void* dgb_host_alloc(uint64_t bytes); /* page-locked host memory, NULL on failure */
+void dgb_host_free(void* p);
+
 /* ---- sources (src/solver.cpp:197-210, 248-256) and probes (new capability) --------------------------- */
 /* Source s overwrites u[0][nodeIdx[offsets[s] .. offsets[s+1])] with amp*sin(2*pi*freq*t+phase) at the start
  * of every step while t < duration. The sine is evaluated on the host in the reference's expression. */

@@ -84,3 +84,32 @@ def test_cli_views_and_receivers(pkg, oracle_mod, mesh_dir, tmp_path):
     for j in range(2):
         for q in range(3):
             assert rel_l2(got[:, 1 + 4 * j + q], ref[:, j, q]) < 1e-10
+
+
+def test_async_snapshot_equals_get_state(pkg, mesh_dir):
+    """dgb_snapshot_begin / _end deliver the state of the moment of `begin`, while the next run is already under way."""
+    import torch
+    model = pkg.Model.make_cube(4, -10.0, 10.0, 4)
+    cfg = pkg.Config()
+    cfg.add_initial_condition(0.0, 0.0, 0.0, 20.0, 1.0)
+    mesh = pkg.Mesh(model, cfg)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(0.0, 0.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * 9))
+    u0 = mesh.initial_condition()
+    for kernel in (0, 4):
+        eng = pkg.Engine(mesh, options={"kernel": kernel})
+        eng.set_state(u0)
+        t = eng.run(pkg.RUNGE_KUTTA, 0.0, 5)
+        want = eng.get_state().copy()
+        snap = torch.empty((4, mesh.N), dtype=torch.float64, pin_memory=True).numpy()
+        eng.snapshot_begin(snap)
+        t = eng.run(pkg.RUNGE_KUTTA, t, 5)  # overlaps the copy
+        eng.snapshot_end()
+        later = eng.get_state()
+        if kernel == 0:
+            assert np.array_equal(snap, want)
+        else:  # Bernstein mode converts on the device: same conversion kernel, same result
+            assert np.array_equal(snap, want)
+        assert not np.array_equal(later, want)
+        with pytest.raises(pkg.DgbError):
+            eng.snapshot_end()  # nothing in flight
+        eng.close()
