@@ -1,9 +1,9 @@
 #!/bin/bash
-# Usage (under gpurun): bash profiles/ab_bench.sh <cells> <variant-name|base> ...   -> one line per variant
+# Usage (under gpurun): [KERNEL=4] bash profiles/ab_bench.sh <cells> <variant-name|base> ...   -> one line per variant (KERNEL: bench.py --kernel)
 CELLS=$1; shift
 for v in "$@"; do
   if [ "$v" = base ]; then unset DGB_LIB; else export DGB_LIB=$PWD/dgfem-acoustic_b200/lib/variants/libdgb_$v.so; fi
-  timeout 300 python bench.py --cells $CELLS --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -2 gpurun_out/ab_$v.err
+  timeout 300 python bench.py --cells $CELLS --steps 8 --warmup 3 --no-cpu-baseline --kernel ${KERNEL:-0} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -2 gpurun_out/ab_$v.err
   python - <<PY
 import json
 try:
