@@ -13,6 +13,7 @@
 // FP64-bound flagship orders use the tiled DMMA kernel in stage_tiled.cu.
 #include "dgb_internal.h"
 #include "dgb_device.cuh"
+#include "dgb_launch.h"  // launches go through DGB_LAUNCH so that the CPU tests can run this file under oracle/cuda_emu.h
 
 namespace dgb {
 
@@ -142,7 +143,7 @@ void launchGeneric(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
     const int threads = ((E * NP + 31) / 32) * 32;
-    stageGenericKernel<DIM, P><<<(nEl + E - 1) / E, threads, 0, s>>>(M, A);
+    DGB_LAUNCH((stageGenericKernel<DIM, P>), (nEl + E - 1) / E, threads, 0, s, M, A);
 }
 
 }  // namespace
@@ -211,21 +212,21 @@ __global__ void unpackElementsKernel(double* y, int64_t stride, int Np, int firs
 }  // namespace
 
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s) {
-    if (n > 0) setNodesKernel<<<(n + 255) / 256, 256, 0, s>>>(field, idx, n, value);
+    if (n > 0) DGB_LAUNCH(setNodesKernel, (n + 255) / 256, 256, 0, s, field, idx, n, value);
 }
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s) {
-    if (n > 0) gatherProbesKernel<<<(4 * n + 255) / 256, 256, 0, s>>>(u, stride, idx, n, out);
+    if (n > 0) DGB_LAUNCH(gatherProbesKernel, (4 * n + 255) / 256, 256, 0, s, u, stride, idx, n, out);
 }
 void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s) {
-    if (n > 0) gatherReceiversKernel<<<(4 * n + 127) / 128, 128, 0, s>>>(u, stride, Np, el, w, n, out);
+    if (n > 0) DGB_LAUNCH(gatherReceiversKernel, (4 * n + 127) / 128, 128, 0, s, u, stride, Np, el, w, n, out);
 }
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s) {
     const int64_t tot = 4ll * n * Np;
-    if (tot > 0) packElementsKernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(y, stride, Np, elems, n, buf);
+    if (tot > 0) DGB_LAUNCH(packElementsKernel, (unsigned)((tot + 255) / 256), 256, 0, s, y, stride, Np, elems, n, buf);
 }
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s) {
     const int64_t tot = 4ll * n * Np;
-    if (tot > 0) unpackElementsKernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(y, stride, Np, firstElem, n, buf);
+    if (tot > 0) DGB_LAUNCH(unpackElementsKernel, (unsigned)((tot + 255) / 256), 256, 0, s, y, stride, Np, firstElem, n, buf);
 }
 
 }  // namespace dgb

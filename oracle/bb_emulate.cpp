@@ -1,18 +1,18 @@
 // Runs the Bernstein-Bezier CUDA kernels (dgfem-acoustic_b200/csrc/stage_bb.cu, the file itself) on the CPU through
 // cuda_emu.h — TEST INFRASTRUCTURE ONLY. The engine's device layout (what dgb_create uploads: Ginv, per-face geometry,
-// neighbour ids, flags, de-duplicated face-node maps) is rebuilt here for one GPU from the desc, following
+// neighbour ids, flags, de-duplicated face-node maps) is rebuilt for one GPU from the desc by emu_layout.h, following
 // csrc/dgb_api.cu (createImpl), so that the kernels see on the host exactly what they see on the device.
 #define DGB_EMULATE 1
 #include "cuda_emu.h"
 
 #include <cstring>
-#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../dgfem-acoustic_b200/csrc/bb_setup.h"
 #include "../dgfem-acoustic_b200/csrc/stage_bb.cu"
+#include "emu_layout.h"
 
 using namespace dgb;
 
@@ -20,12 +20,10 @@ namespace {
 thread_local std::string g_err;
 
 struct Emu {
-    DeviceMesh M{};
+    emu::Layout L;
+    DeviceMesh& M = L.M;
     bb::Setup S;
     StageKernel kernel;
-    std::vector<double> Ginv, fgeo;
-    std::vector<int32_t> fnbr, fflags, faceNodes;
-    std::vector<uint8_t> maps;
     int Np = 0, K = 0;
     double dt = 0;
 };
@@ -34,64 +32,9 @@ Emu* build(const dgb_desc* d, int variant) {
     auto* E = new Emu;
     try {
         E->S = bb::buildSetup(d);
-        const int Np = d->Np, Nfp = d->Nfp, Nf = d->Nf, K = d->K, gE = d->nGeomEl, gF = d->nGeomF;
-        E->Np = Np; E->K = K; E->dt = d->dt;
-        E->faceNodes = E->S.faceNodes;
-        E->Ginv.resize((size_t)K * 9); E->fgeo.resize((size_t)K * Nf * 4); E->fnbr.resize((size_t)K * Nf); E->fflags.resize((size_t)K * Nf);
-        std::map<std::vector<uint8_t>, int> mapIds;
-        std::vector<int> pos(Np, -1);
-        for (int el = 0; el < K; ++el) {
-            const double* J = &d->elJacobian[(size_t)el * gE * 9];
-            double A[3][3], B[3][3];
-            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[r][c] = J[r * 3 + c];
-            const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
-                               A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    const int r1 = (c + 1) % 3, r2 = (c + 2) % 3, c1 = (r + 1) % 3, c2 = (r + 2) % 3;
-                    B[r][c] = (A[r1][c1] * A[r2][c2] - A[r1][c2] * A[r2][c1]) / det;
-                }
-            for (int x = 0; x < 3; ++x) for (int u = 0; u < 3; ++u) E->Ginv[(size_t)el * 9 + x * 3 + u] = B[x][u];
-            const double detE = d->elJacobianDet[(size_t)el * gE];
-            for (int lf = 0; lf < Nf; ++lf) {
-                const int f = d->elFId[(size_t)el * Nf + lf];
-                const int side = d->fNbrElId[2 * (size_t)f] == el ? 0 : 1;
-                const int o = d->elFOrientation[(size_t)el * Nf + lf];
-                double* fg = &E->fgeo[((size_t)el * Nf + lf) * 4];
-                for (int x = 0; x < 3; ++x) fg[x] = o * d->fNormal[(size_t)f * gF * 3 + x];
-                fg[3] = d->fJacobianDet[(size_t)f * gF] / detE;
-                int flags;
-                if (d->fIsBoundary[f]) {
-                    flags = d->fBC[f] == 1 ? FACE_REFLECTING : FACE_ABSORBING;
-                    E->fnbr[(size_t)el * Nf + lf] = -1;
-                } else {
-                    E->fnbr[(size_t)el * Nf + lf] = d->fNbrElId[2 * (size_t)f + (1 - side)];
-                    const int tau = d->fc * o * (side == 0 ? 1 : -1);
-                    flags = FACE_INTERIOR | (tau < 0 ? FLAG_TAU_NEG : 0);
-                }
-                std::fill(pos.begin(), pos.end(), -1);
-                for (int m = 0; m < Nfp; ++m) pos[E->faceNodes[lf * Nfp + m]] = m;
-                std::vector<uint8_t> mp(Nfp, 0);
-                for (int n = 0; n < Nfp; ++n) {
-                    const int own = d->fNToElNId[((size_t)f * Nfp + n) * 2 + side];
-                    const int nb = d->fIsBoundary[f] ? own : d->fNToElNId[((size_t)f * Nfp + n) * 2 + (1 - side)];
-                    mp[pos[own]] = (uint8_t)nb;
-                }
-                auto it = mapIds.find(mp);
-                if (it == mapIds.end()) {
-                    it = mapIds.emplace(mp, (int)mapIds.size()).first;
-                    E->maps.insert(E->maps.end(), mp.begin(), mp.end());
-                }
-                E->fflags[(size_t)el * Nf + lf] = flags | (it->second << FLAG_MAP_SHIFT);
-            }
-        }
-        DeviceMesh& M = E->M;
-        M.dim = 3; M.order = d->order; M.Np = Np; M.Nfp = Nfp; M.Nf = Nf; M.L = 3 * Np + Nf * Nfp;
-        M.Kown = M.Ktot = K;
-        M.stride = (int64_t)K * Np;
-        M.faceNodes = E->faceNodes.data(); M.nbrMaps = E->maps.data(); M.nMaps = (int)mapIds.size();
-        M.Ginv = E->Ginv.data(); M.fgeo = E->fgeo.data(); M.fnbr = E->fnbr.data(); M.fflags = E->fflags.data();
-        M.c0 = d->c0; M.rho0 = d->rho0; M.v0[0] = d->v0[0]; M.v0[1] = d->v0[1]; M.v0[2] = d->v0[2];
+        E->Np = d->Np; E->K = d->K; E->dt = d->dt;
+        emu::build(d, E->L);  // what dgb_create uploads
+        if (E->L.faceNodes != E->S.faceNodes) throw std::runtime_error("face-node tables disagree");
         setBBTables(d->order, E->S.T);
         E->kernel = selectBBKernel(3, d->order, variant);
         if (!E->kernel.launch) throw std::runtime_error("no Bernstein kernel for this order");

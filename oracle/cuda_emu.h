@@ -44,6 +44,8 @@ static cuemu::Idx blockDim, gridDim;
 
 #define __syncthreads() cuemu::syncthreads()
 inline double __dmul_rn(double a, double b) { return a * b; }
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
 using std::max;
 using std::min;
 
