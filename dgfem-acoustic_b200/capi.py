@@ -51,7 +51,7 @@ class DgfConfig(C.Structure):
         ("nSources", C.c_int32), ("sources", (C.c_double * 9) * 64),
         ("nInit", C.c_int32), ("initConditions", (C.c_double * 6) * 32),
         ("nPhysBC", C.c_int32), ("physBCTag", C.c_int32 * 64), ("physBCType", C.c_int32 * 64),
-        ("nReceivers", C.c_int32), ("receivers", (C.c_double * 3) * 64), ("receiverFile", C.c_char * 512),
+        ("nReceivers", C.c_int32), ("receivers", (C.c_double * 3) * 64), ("receiverFile", C.c_char * 512), ("receiverWav", C.c_char * 512),
     ]
 
 

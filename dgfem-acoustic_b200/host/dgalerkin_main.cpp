@@ -121,6 +121,10 @@ int main(int argc, char** argv) {
         if (dgf_write_receivers(cfg.receiverFile, cfg.nReceivers, &cfg.receivers[0][0], nrec, cfg.timeStart, cfg.timeStep, rcvRec.data()) != 0)
             std::fprintf(stderr, "Error   : %s\n", dgf_last_error());
         else std::printf("Info    : %d receiver(s), %d samples -> %s\n", cfg.nReceivers, nrec, cfg.receiverFile);
+        for (int j = 0; cfg.receiverWav[0] && j < cfg.nReceivers && nrec > 0; ++j) {  // receiver audio, like the reference's assets/
+            const std::string wav = std::string(cfg.receiverWav) + std::to_string(j) + ".wav";
+            if (dgf_write_wav(wav.c_str(), cfg.nReceivers, j, 0, nrec, cfg.timeStep, 0, rcvRec.data()) != 0) std::fprintf(stderr, "Error   : %s\n", dgf_last_error());
+        }
     }
     std::printf("Info    : %lld kernel launches, last chunk %.3f ms on the device\n", (long long)dgb_launch_count(h), dgb_last_run_ms(h));
     dgf_write_views(cfg.saveFile, model, mesh, &cfg, (int)snapStep.size(), snapStep.data(), snapTime.data(), snapU.data());

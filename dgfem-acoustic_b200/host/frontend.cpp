@@ -204,6 +204,8 @@ extern "C" int dgf_parse_config(const char* path, const dgf_model* model, dgf_co
                 for (int k = 1; k <= 5; ++k) q[k] = std::stod(sep[k]);
             } else if (it.first == "receiverFile") {
                 std::snprintf(c->receiverFile, sizeof c->receiverFile, "%s", it.second.c_str());
+            } else if (it.first == "receiverWav") {
+                std::snprintf(c->receiverWav, sizeof c->receiverWav, "%s", it.second.c_str());
             } else if (it.first.rfind("receiver", 0) == 0) {  // not a key of the reference: it skips it
                 auto sep = splitCsv(it.second);
                 if (sep.size() < 3) throw std::runtime_error("receiver needs 3 comma-separated coordinates: " + it.first);

@@ -38,10 +38,12 @@ typedef struct dgf_config {
     int32_t physBCType[DGF_MAX_PHYS]; /* 0 "Absorbing", 1 "Reflecting" */
     /* Receivers — keys the reference's parser ignores (it only looks at `source*`,
      * `initialCondtition*` and the physical-group names, configParser.cpp:65-132), so one file serves both programs:
-     *   receiver<name> = x, y, z      (std::map order of the keys)      receiverFile = path   (default receivers.txt) */
+     *   receiver<name> = x, y, z      (std::map order of the keys)      receiverFile = path   (default receivers.txt)
+     *   receiverWav = prefix          (optional: the pressure at receiver j as 16-bit PCM, <prefix><j>.wav, rate 1/timeStep) */
     int32_t nReceivers;
     double receivers[DGF_MAX_RECEIVERS][3];
     char receiverFile[512];
+    char receiverWav[512];
 } dgf_config;
 
 const char* dgf_last_error(void);

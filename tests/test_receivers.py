@@ -105,12 +105,12 @@ def test_oracle_receivers_against_probes_and_interpolated_state(pkg, oracle_mod,
 def test_config_keys_and_writers(pkg, mesh_dir, config_dir, tmp_path):
     conf = tmp_path / "rcv.conf"
     conf.write_text((config_dir / "square_pulse.conf").read_text() +
-                    "\nreceiverB = 1.0, -2.0, 0.0\nreceiverA = 0.5, 0.25, 0.0\nreceiverFile = out_rcv.txt\n")
+                    "\nreceiverB = 1.0, -2.0, 0.0\nreceiverA = 0.5, 0.25, 0.0\nreceiverFile = out_rcv.txt\nreceiverWav = mic_\n")
     model = pkg.Model.open_msh(mesh_dir / "square.msh", 1)
     cfg = model.parse_config(conf)
     assert cfg.c.nReceivers == 2
     assert cfg.receivers == [[0.5, 0.25, 0.0], [1.0, -2.0, 0.0]]  # std::map order of the keys
-    assert cfg.c.receiverFile == b"out_rcv.txt"
+    assert cfg.c.receiverFile == b"out_rcv.txt" and cfg.c.receiverWav == b"mic_"
     assert cfg.c.nSources == 0 and cfg.c.nInit == 1  # the reference's keys are parsed as before
     # the stock config has no receivers
     assert model.parse_config(config_dir / "square_pulse.conf").c.nReceivers == 0
