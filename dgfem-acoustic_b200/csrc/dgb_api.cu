@@ -136,6 +136,7 @@ struct dgb_handle {
     StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, active;
     // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
     bool bbMode = false;
+    int bbTile = 32;                 // elements per CTA of the Bernstein kernels (32, 16, 8)
     std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
     // curved (non-affine) meshes: the reference's own tables on the device + inverse element mass matrices; every
     // element then goes through stage_curved.cu
@@ -1326,6 +1327,17 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             if (value == 1) setupP2P(h);
             h->exchangeMode = value;
         } else if (k == "p2p_timeout_ms") h->p2pTimeoutMs = std::max(1, value);
+        else if (k == "bb_tile") {  // elements per CTA of the Bernstein kernels; takes effect at once if one of them is active
+            if (value != 8 && value != 16 && value != 32) throw DgbException(DGB_ERR_ARG, "bb_tile must be 8, 16 or 32");
+            if (h->bbKernel.launch) {
+                const bool a = h->active.launch == h->bbKernel.launch, b = h->active.launch == h->bbSeqKernel.launch;
+                h->bbKernel = selectBBKernel(h->M.dim, h->M.order, 0, value);
+                h->bbSeqKernel = selectBBKernel(h->M.dim, h->M.order, 1, value);
+                if (a) h->active = h->bbKernel;
+                if (b) h->active = h->bbSeqKernel;
+            }
+            h->bbTile = value;
+        }
         else if (k == "sm_reserve") h->smReserve = std::max(0, value);
         else if (k == "graph") h->useGraph = value < 0 ? -1 : (value ? 1 : 0);
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;

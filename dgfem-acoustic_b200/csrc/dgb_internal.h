@@ -67,7 +67,7 @@ struct StageKernel {
 StageKernel selectGenericKernel(int dim, int order);
 StageKernel selectTiledKernel(int dim, int order);  // launch == nullptr if no tiled instance exists
 StageKernel selectWsKernel(int dim, int order);     // warp-specialised DMMA kernel, zero mean flow only (stage_ws.cu)
-StageKernel selectBBKernel(int dim, int order, int variant = 0);  // Bernstein-Bezier sparse-operator kernel, tetrahedra (stage_bb.cu); the state holds Bernstein coefficients; variant 1: the faces one after the other
+StageKernel selectBBKernel(int dim, int order, int variant = 0, int tile = 32);  // Bernstein-Bezier sparse-operator kernel, tetrahedra (stage_bb.cu); the state holds Bernstein coefficients; variant 1: the faces one after the other; tile: elements per CTA (32, 16, 8)
 // permutation tables of the Bernstein kernel for one order (constant memory of the current device; they depend only on the
 // element's node numbering convention, so one copy per order serves every handle of the process)
 void setBBTables(int order, const bb::Tables& T);

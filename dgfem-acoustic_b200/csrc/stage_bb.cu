@@ -48,14 +48,10 @@ __host__ __device__ constexpr int conflictFreeStride(int n, int elemStride) {
     return n;
 }
 
-template <int P>
+template <int P, int TE_>
 struct BBCfg {
     static constexpr int NP = bb::tet(P), NFP = bb::tri(P), NFL = 4 * NFP;
-#ifdef DGB_BB_TE
-    static constexpr int TE = DGB_BB_TE;  // elements per CTA
-#else
-    static constexpr int TE = 32;
-#endif
+    static constexpr int TE = TE_;          // elements per CTA: 32 (4 warps), 16, or 8 (one warp: the barriers become warp-local)
     static constexpr int THREADS = 4 * TE;  // == (element, face) pairs == (element, field) pairs of a tile
     static constexpr int SQ = conflictFreeStride(TE * NP, NP);    // field stride of the coefficient tile
     static constexpr int SF = conflictFreeStride(TE * NFL, NFL);  // field stride of the face-input tile
@@ -83,9 +79,9 @@ __device__ __forceinline__ void cpAsyncWaitAll() {
 #endif
 }
 
-template <int P>
-__global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M, StageArgs A) {
-    using C = BBCfg<P>;
+template <int P, int TE_>
+__global__ void __launch_bounds__(BBCfg<P, TE_>::THREADS) stageBBKernel(DeviceMesh M, StageArgs A) {
+    using C = BBCfg<P, TE_>;
     constexpr int NP = C::NP, NFP = C::NFP, NFL = C::NFL, TE = C::TE;
     static_assert(bb::BC_INTERIOR == FACE_INTERIOR && bb::BC_ABSORBING == FACE_ABSORBING && bb::BC_REFLECTING == FACE_REFLECTING, "face codes");
     DGB_DYNAMIC_SMEM(double, smem);
@@ -215,19 +211,19 @@ __global__ void __launch_bounds__(BBCfg<P>::THREADS) stageBBKernel(DeviceMesh M,
 // per element and field at order 4), so a tile needs about half the shared memory and more CTAs fit an SM; the lift body is
 // shared by the four faces (a run-time loop; only the scatter into the element's coefficients is face-specific), which also
 // shrinks the code. Costs two more barriers per face. dgb_set_option("bb_variant", 1).
-template <int P>
+template <int P, int TE_>
 struct BBSeqCfg {
     static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
-    static constexpr int TE = BBCfg<P>::TE, THREADS = 4 * TE;
+    static constexpr int TE = TE_, THREADS = 4 * TE;
     static constexpr int SQ = conflictFreeStride(TE * NP, NP);
     static constexpr int SX = conflictFreeStride(TE * NFP, NFP);  // field stride of the one-face input tile
     static constexpr int FC = 8;
     static constexpr size_t SMEM = (size_t)(4 * (SQ + SX) + THREADS * FC) * sizeof(double) + (size_t)2 * THREADS * sizeof(int);
 };
 
-template <int P>
-__global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceMesh M, StageArgs A) {
-    using C = BBSeqCfg<P>;
+template <int P, int TE_>
+__global__ void __launch_bounds__(BBSeqCfg<P, TE_>::THREADS) stageBBSeqKernel(DeviceMesh M, StageArgs A) {
+    using C = BBSeqCfg<P, TE_>;
     constexpr int NP = C::NP, NFP = C::NFP, TE = C::TE;
     DGB_DYNAMIC_SMEM(double, smem);
     double* sQ = smem;                       // [4][SQ]   coefficients of the tile, at the end the result
@@ -363,34 +359,34 @@ __global__ void __launch_bounds__(BBSeqCfg<P>::THREADS) stageBBSeqKernel(DeviceM
     }
 }
 
-template <int P>
+template <int P, int TE_>
 void launchBBSeq(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
-    using C = BBSeqCfg<P>;
+    using C = BBSeqCfg<P, TE_>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
 #ifndef DGB_EMULATE
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(stageBBSeqKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(stageBBSeqKernel<P, TE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         configured = true;
     }
 #endif
-    DGB_LAUNCH(stageBBSeqKernel<P>, (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
+    DGB_LAUNCH((stageBBSeqKernel<P, TE_>), (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }
 
-template <int P>
+template <int P, int TE_>
 void launchBB(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
-    using C = BBCfg<P>;
+    using C = BBCfg<P, TE_>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
 #ifndef DGB_EMULATE
     static bool configured = false;  // one device per process
     if (!configured) {
-        cudaFuncSetAttribute(stageBBKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(stageBBKernel<P, TE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         configured = true;
     }
 #endif
-    DGB_LAUNCH(stageBBKernel<P>, (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
+    DGB_LAUNCH((stageBBKernel<P, TE_>), (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }
 
 // y = Mat x per element and field (nodal <-> Bernstein conversion of a whole state array); in and out may alias
@@ -443,17 +439,19 @@ __global__ void __launch_bounds__(64) setNodesBBKernel(double* field, int Np, co
 
 }  // namespace
 
-StageKernel selectBBKernel(int dim, int order, int variant) {
+StageKernel selectBBKernel(int dim, int order, int variant, int tile) {
     StageKernel k;
-    if (dim != 3) return k;
-#define DGB_CASE(P)                                                                                     \
-    if (order == P) {                                                                                   \
-        if (variant == 1) { k.launch = &launchBBSeq<P>; k.name = "stage_bb_seq<3," #P ">"; }            \
-        else { k.launch = &launchBB<P>; k.name = "stage_bb<3," #P ">"; }                                \
-        return k;                                                                                       \
+    if (dim != 3 || (tile != 8 && tile != 16 && tile != 32)) return k;
+#define DGB_CASE_T(P, T)                                                                                        \
+    if (order == P && tile == T) {                                                                              \
+        if (variant == 1) { k.launch = &launchBBSeq<P, T>; k.name = "stage_bb_seq<3," #P ">/" #T; }             \
+        else { k.launch = &launchBB<P, T>; k.name = "stage_bb<3," #P ">/" #T; }                                 \
+        return k;                                                                                               \
     }
+#define DGB_CASE(P) DGB_CASE_T(P, 32) DGB_CASE_T(P, 16) DGB_CASE_T(P, 8)
     DGB_CASE(2) DGB_CASE(3) DGB_CASE(4) DGB_CASE(5)
 #undef DGB_CASE
+#undef DGB_CASE_T
     return k;
 }
 

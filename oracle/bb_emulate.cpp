@@ -18,6 +18,7 @@ using namespace dgb;
 
 namespace {
 thread_local std::string g_err;
+int g_tile = 32;  // elements per CTA (bbe_set_tile)
 
 struct Emu {
     emu::Layout L;
@@ -36,7 +37,7 @@ Emu* build(const dgb_desc* d, int variant) {
         emu::build(d, E->L);  // what dgb_create uploads
         if (E->L.faceNodes != E->S.faceNodes) throw std::runtime_error("face-node tables disagree");
         setBBTables(d->order, E->S.T);
-        E->kernel = selectBBKernel(3, d->order, variant);
+        E->kernel = selectBBKernel(3, d->order, variant, g_tile);
         if (!E->kernel.launch) throw std::runtime_error("no Bernstein kernel for this order");
         return E;
     } catch (...) {
@@ -49,6 +50,7 @@ Emu* build(const dgb_desc* d, int variant) {
 extern "C" {
 
 const char* bbe_last_error(void) { return g_err.c_str(); }
+void bbe_set_tile(int tile) { g_tile = tile; }
 
 // nodal u -> rhs = L(u) (MODE_RHS) with the emulated kernel `variant` (0: stage_bb, 1: stage_bb_seq)
 int bbe_eval_rhs(const dgb_desc* d, int variant, const double* u, double* rhs) {

@@ -44,10 +44,11 @@ def _case(pkg, mesh_dir, name, order, v0):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("name,order,v0", [("cube:3", 4, (0.0, 0.0, 0.0)), ("cube:3", 3, (30.0, 10.0, -5.0)), ("cube:4", 2, (0.0, 0.0, 0.0)),
-                                           ("cube:2", 5, (1.0, 2.0, 3.0)), ("cube.msh", 3, (0.0, 0.0, 0.0))])
-def test_emulated_kernels_equal_the_oracle(pkg, oracle_mod, bbe, mesh_dir, name, order, v0, variant):
+@pytest.mark.parametrize("name,order,v0,tile", [("cube:3", 4, (0.0, 0.0, 0.0), 32), ("cube:3", 3, (30.0, 10.0, -5.0), 16), ("cube:4", 2, (0.0, 0.0, 0.0), 8),
+                                                ("cube:2", 5, (1.0, 2.0, 3.0), 32), ("cube.msh", 3, (0.0, 0.0, 0.0), 32), ("cube:3", 4, (3.0, 2.0, 1.0), 8)])
+def test_emulated_kernels_equal_the_oracle(pkg, oracle_mod, bbe, mesh_dir, name, order, v0, tile, variant):
     mesh, u = _case(pkg, mesh_dir, name, order, v0)
+    bbe.bbe_set_tile(tile)  # elements per CTA: 32, 16 or 8 (dgb_set_option("bb_tile", ...))
     d = C.cast(mesh.desc_p, C.c_void_p)
     orc = oracle_mod.Oracle(mesh)
     orc.set_sources_from_config()

@@ -45,8 +45,9 @@ def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     mesh = _mesh(pkg, mesh_dir, name, order, v0)
     u0 = _state(mesh)
     orc = oracle_mod.Oracle(mesh)
-    eng = pkg.Engine(mesh, options={"kernel": variant})
-    assert eng.kernel_name == (f"stage_bb<3,{order}>" if variant == 4 else f"stage_bb_seq<3,{order}>")
+    tile = {2: 8, 3: 16}.get(order, 32)
+    eng = pkg.Engine(mesh, options={"bb_tile": tile, "kernel": variant})
+    assert eng.kernel_name == (f"stage_bb<3,{order}>/{tile}" if variant == 4 else f"stage_bb_seq<3,{order}>/{tile}")
     rhs = eng.eval_rhs(u0)
     ref = orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u0)
     for q in range(4):
