@@ -91,7 +91,7 @@ saveFile=out
 """
 
 
-@pytest.mark.parametrize("mesh_name,order,warp", [("square.msh", 3, (0.15, 0.9)), ("cube.msh", 2, (0.2, 0.4))])
+@pytest.mark.parametrize("mesh_name,order,warp", [("square.msh", 3, (0.15, 0.9)), ("gen:cube4", 2, (0.3, 0.4)), ("gen:cube2", 3, (0.4, 0.3))])
 def test_curved_elements_faithful_oracle_equals_the_reference(pkg, oracle_mod, mesh_dir, tmp_path, mesh_name, order, warp):
     """SURVEY §8 f3 groundwork: on a curved (warped isoparametric) mesh the reference keeps one Jacobian / normal per
     integration point; the front end produces that layout (nGeomEl = nG, nGeomF = nGf) and the oracle's faithful mode —
@@ -100,10 +100,15 @@ def test_curved_elements_faithful_oracle_equals_the_reference(pkg, oracle_mod, m
     conf = tmp_path / "case.conf"
     text = CONF_CURVED if mesh_name == "square.msh" else CONF_CURVED.replace("v0_z = 0", "v0_z = 2")
     conf.write_text(text)
+    if mesh_name.startswith("gen:cube"):  # a small generated cube, written as an order-1 MSH file for the reference
+        msh = tmp_path / "cube.msh"
+        pkg.Model.make_cube(int(mesh_name[8:]), -10.0, 10.0, 1).write_msh(msh)
+    else:
+        msh = mesh_dir / mesh_name
     env = dict(os.environ, GMSHLITE_QUIET="1", GMSHLITE_ORDER=str(order), GMSHLITE_WARP=f"{warp[0]},{warp[1]}", OMP_NUM_THREADS="2")
-    subprocess.run([str(REF_BIN), str(mesh_dir / mesh_name), str(conf)], cwd=tmp_path, env=env, check=True, timeout=900)
+    subprocess.run([str(REF_BIN), str(msh), str(conf)], cwd=tmp_path, env=env, check=True, timeout=900)
     P, V = read_view(tmp_path / "out.Pressure.bin"), read_view(tmp_path / "out.Velocity.bin")
-    model = pkg.Model.open_msh(mesh_dir / mesh_name, order).warp(*warp)
+    model = pkg.Model.open_msh(msh, order).warp(*warp)
     cfg = model.parse_config(conf)
     mesh = pkg.Mesh(model, cfg)
     assert mesh.desc.nGeomEl == mesh.desc.nG and mesh.desc.nGeomF == mesh.desc.nGf
