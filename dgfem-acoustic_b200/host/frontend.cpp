@@ -608,16 +608,10 @@ extern "C" int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double
         const dgb_desc& d = mesh->d;
         const int dim = d.dim, Np = d.Np;
         const gml::RefElement& ref = gml::refElement(dim, d.order);
-        const double* u0 = &ref.uvw[0];  // parametric coordinates of local node 0
         const double X[3] = {x, y, z};
-        int best = -1;
-        double bestViol = 1e300, bestU[3] = {0, 0, 0};
-        for (int el = 0; el < d.K; ++el) {
-            // x = x_node0 + sum_u (u_u - u0_u) J_u ,  J_u = elJacobian[el][u*3 + .] ; least squares for elements embedded in 3D
-            const double* J = &mesh->elJacobian[(size_t)el * d.nGeomEl * 9];
-            const double* x0 = &mesh->nodeCoords[(size_t)el * Np * 3];
-            double r[3] = {X[0] - x0[0], X[1] - x0[1], X[2] - x0[2]};
-            double G[3][3], b[3], du[3] = {0, 0, 0};
+        // du = argmin | r - sum_a du_a J_a | for the dim tangent vectors J_a (rows of 3): normal equations, Cramer
+        auto lsq = [dim](const double* J, const double* r, double* du) {
+            double G[3][3], b[3];
             for (int a = 0; a < dim; ++a) {
                 b[a] = dot3(&J[a * 3], r);
                 for (int c = 0; c < dim; ++c) G[a][c] = dot3(&J[a * 3], &J[c * 3]);
@@ -630,16 +624,16 @@ extern "C" int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double
             } else {
                 const double det = G[0][0] * (G[1][1] * G[2][2] - G[1][2] * G[2][1]) - G[0][1] * (G[1][0] * G[2][2] - G[1][2] * G[2][0]) +
                                    G[0][2] * (G[1][0] * G[2][1] - G[1][1] * G[2][0]);
-                for (int k = 0; k < 3; ++k) {  // Cramer
+                for (int k = 0; k < 3; ++k) {
                     double A[3][3];
                     for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) A[a][c] = c == k ? b[a] : G[a][c];
                     du[k] = (A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
                              A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) / det;
                 }
             }
-            double u[3] = {0, 0, 0};
-            for (int a = 0; a < dim; ++a) u[a] = u0[a] + du[a];
-            // barycentric coordinates: line on [-1,1], unit triangle / tetrahedron
+        };
+        // how far outside the reference element: line on [-1,1], unit triangle / tetrahedron (0 inside)
+        auto violation = [dim](const double* u) {
             double lmin;
             if (dim == 1) lmin = std::min(0.5 * (1 - u[0]), 0.5 * (1 + u[0]));
             else {
@@ -648,7 +642,42 @@ extern "C" int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double
                 for (int a = 0; a < dim; ++a) { l0 -= u[a]; lmin = std::min(lmin, u[a]); }
                 lmin = std::min(lmin, l0);
             }
-            const double viol = lmin >= -1e-12 ? 0.0 : -lmin;
+            return lmin >= -1e-12 ? 0.0 : -lmin;
+        };
+        const bool curved = d.nGeomEl > 1;  // one Jacobian per integration point: the elements may be curved
+        std::vector<double> phi(Np), dphi((size_t)Np * 3);
+        int best = -1;
+        double bestViol = 1e300, bestU[3] = {0, 0, 0};
+        for (int el = 0; el < d.K; ++el) {
+            const double* xn = &mesh->nodeCoords[(size_t)el * Np * 3];
+            double u[3] = {0, 0, 0}, J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            // straight-sided map through the vertices (the first dim+1 nodes): x = x_0 + sum_a (u_a - u0_a) J_a
+            for (int a = 0; a < dim; ++a)
+                for (int c = 0; c < 3; ++c) J[a * 3 + c] = (xn[3 * (a + 1) + c] - xn[c]) * (dim == 1 ? 0.5 : 1.0);
+            const double r0[3] = {X[0] - xn[0], X[1] - xn[1], X[2] - xn[2]};
+            double du[3] = {0, 0, 0};
+            lsq(J, r0, du);
+            for (int a = 0; a < dim; ++a) u[a] = ref.uvw[a] + du[a];
+            double viol = violation(u);
+            if (curved && viol < 0.5) {
+                // Newton on the isoparametric map x(u) = sum_n phi_n(u) x_n from the straight-sided guess
+                for (int it = 0; it < 20; ++it) {
+                    ref.basis(u, phi.data());
+                    ref.gradBasis(u, dphi.data());
+                    double r[3] = {X[0], X[1], X[2]};
+                    for (int k = 0; k < 9; ++k) J[k] = 0.0;
+                    for (int n = 0; n < Np; ++n)
+                        for (int c = 0; c < 3; ++c) {
+                            r[c] -= phi[n] * xn[3 * n + c];
+                            for (int a = 0; a < dim; ++a) J[a * 3 + c] += dphi[3 * n + a] * xn[3 * n + c];
+                        }
+                    lsq(J, r, du);
+                    double step = 0;
+                    for (int a = 0; a < dim; ++a) { u[a] += du[a]; step = std::max(step, std::fabs(du[a])); }
+                    if (step < 1e-14) break;
+                }
+                viol = violation(u);
+            }
             if (viol < bestViol) {
                 bestViol = viol; best = el;
                 std::copy(u, u + 3, bestU);

@@ -94,7 +94,8 @@ int dgf_nearest_node(const dgf_mesh* mesh, double x, double y, double z);
 /* Receivers: finds the element that contains (x,y,z) — the lowest element id if the point lies on
  * a shared face / edge / vertex; if the point is outside the mesh, the element it violates least, with *outside = 1 —
  * and evaluates that element's Np Lagrange basis functions at the point (weights[Np]; uvw[3] optional = the
- * parametric coordinates). Straight-sided elements (the affine inverse map). Returns the element id, -1 on error. */
+ * parametric coordinates). Straight-sided elements: the affine inverse map; curved ones: Newton on the isoparametric map.
+ * Returns the element id, -1 on error. */
 int dgf_locate_point(const dgf_mesh* mesh, double x, double y, double z, double* weights, double* uvw, int* outside);
 /* Receiver time series as text: one line per step, `t  p vx vy vz` per receiver; a header names the points.
  * rec is [nsteps][nrecv][4] as dgb_get_receivers returns it; t_k accumulates t += dt like the loop header. */

@@ -179,3 +179,25 @@ def test_engine_receivers_match_the_oracle(pkg, oracle_mod, mesh_dir, config_dir
         assert rel_l2(rec[:, :, q], rec_ref[:, :, q]) < 1e-10
     assert np.abs(rec[:, 0] - rec_probe[:, 0]).max() <= 1e-13 * max(1.0, np.abs(rec_probe).max())
     eng.close()
+
+
+@pytest.mark.parametrize("name,order,warp", [("square.msh", 3, (0.15, 0.9)), ("cube:3", 2, (0.3, 0.4)), ("cube:2", 4, (0.4, 0.3))])
+def test_point_location_on_curved_meshes(pkg, mesh_dir, name, order, warp):
+    """Curved (warped isoparametric) elements: Newton on x(u) = sum_n phi_n(u) x_n — the located parametric point maps back to
+    the physical point, the weights are a partition of unity and reproduce the (isoparametric) coordinate functions."""
+    model = pkg.Model.make_cube(int(name.split(":")[1]), -10.0, 10.0, order) if name.startswith("cube:") else pkg.Model.open_msh(mesh_dir / name, order)
+    model.warp(*warp)
+    mesh = pkg.Mesh(model, pkg.Config())
+    x = mesh.node_coords.reshape(mesh.K, mesh.Np, 3)
+    rng = np.random.default_rng(3)
+    nv = mesh.dim + 1
+    for _ in range(20):
+        el = int(rng.integers(mesh.K))
+        lam = rng.dirichlet(np.ones(nv) * 2.0)
+        pt = lam @ x[el, :nv]  # near element el (inside its straight-sided shadow); some element of the curved mesh contains it
+        got_el, w, uvw, outside = mesh.locate_point(*pt)
+        if outside:  # a point of the shadow that the warped boundary left outside the mesh
+            continue
+        assert abs(w.sum() - 1.0) < 1e-12
+        assert np.abs(w @ x[got_el] - pt).max() < 1e-10 * 10
+        assert uvw[: mesh.dim].min() > -1e-9 and uvw[: mesh.dim].sum() < 1 + 1e-9
