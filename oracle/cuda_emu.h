@@ -53,7 +53,7 @@ namespace cuemu {
 template <typename Kernel, typename... Args>
 void launch(Kernel kernel, unsigned grid, unsigned block, size_t smemBytes, Args... args) {
     State st;
-    st.smem.assign(smemBytes / sizeof(double) + 16, 0.0);
+    st.smem.assign((smemBytes + sizeof(double) - 1) / sizeof(double) + (smemBytes == 0 ? 1 : 0), 0.0);  // exact size: AddressSanitizer builds see overruns
     pthread_barrier_init(&st.barrier, nullptr, block);
     current() = &st;
     blockDim.x = block;

@@ -1,4 +1,4 @@
-"""Shared-memory race check of the emulated CUDA kernels on the CPU: the emulation of oracle/cuda_emu.h runs one OS thread per
+"""Shared-memory race check (and out-of-bounds check) of the emulated CUDA kernels on the CPU: the emulation of oracle/cuda_emu.h runs one OS thread per
 CUDA thread with a pthread barrier for __syncthreads, so a ThreadSanitizer build of an emulation harness sees a missing barrier
 as a data race on the shared-memory buffer — what compute-sanitizer's racecheck reports on the GPU. The check is itself
 checked: a copy of stage_bb.cu with one barrier removed must be reported.
@@ -25,7 +25,16 @@ def _libtsan():
         return None
 
 
+def _libasan():
+    try:
+        p = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+        return p if os.path.isabs(p) and Path(p).exists() else None
+    except Exception:
+        return None
+
+
 TSAN = _libtsan()
+ASAN = _libasan()
 pytestmark = pytest.mark.skipif(TSAN is None, reason="libtsan not available")
 
 
@@ -34,8 +43,8 @@ def _cuda_include():
     return Path(nvcc).resolve().parent.parent / "include"
 
 
-def _build(src_root, harness, out):
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-pthread", "-fsanitize=thread", "-Wno-unknown-pragmas",
+def _build(src_root, harness, out, sanitizer="thread"):
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-pthread", f"-fsanitize={sanitizer}", "-Wno-unknown-pragmas",
            f"-I{src_root / 'include'}", f"-I{_cuda_include()}", str(src_root / "oracle" / harness), "-o", str(out)]
     subprocess.run(cmd, check=True, timeout=900)
 
@@ -70,3 +79,16 @@ def test_the_race_check_sees_a_missing_barrier(tmp_path):
     lib = tmp_path / "libbb_broken_tsan.so"
     _build(root, "bb_emulate.cpp", lib)
     assert _run("bb", lib) > 0
+
+
+@pytest.mark.skipif(ASAN is None, reason="libasan not available")
+@pytest.mark.parametrize("kind,harness", [("bb", "bb_emulate.cpp"), ("curved", "curved_emulate.cpp"), ("generic", "generic_emulate.cpp")])
+def test_no_out_of_bounds_access_in_the_emulated_kernels(tmp_path, kind, harness):
+    """AddressSanitizer build: the emulation sizes the dynamic shared memory exactly and the global arrays are host vectors, so an
+    index that runs off a tile, a state array or a table is reported (the CPU counterpart of compute-sanitizer memcheck)."""
+    lib = tmp_path / f"lib{kind}_asan.so"
+    _build(ROOT, harness, lib, sanitizer="address")
+    env = dict(os.environ, LD_PRELOAD=ASAN, ASAN_OPTIONS="detect_leaks=0:halt_on_error=0", OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, str(WORKER), kind, str(lib)], env=env, capture_output=True, text=True, timeout=1200)
+    assert "worker done" in p.stdout, p.stderr[-2000:]
+    assert "ERROR: AddressSanitizer" not in p.stderr, p.stderr[-3000:]
