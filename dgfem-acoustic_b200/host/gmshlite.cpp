@@ -431,7 +431,7 @@ void Model::addElements(int dim, int entityTag, int type, const std::vector<int>
 }
 
 // =============================================================================================
-// MSH 4.0 ASCII reader
+// MSH ASCII reader (4.0, 4.1, 2.2)
 // =============================================================================================
 Model readMsh(const std::string& path) {
     std::ifstream in(path);
@@ -449,6 +449,7 @@ Model readMsh(const std::string& path) {
         if (!std::getline(in, line)) throw std::runtime_error(std::string("gmshlite: unexpected end of file in ") + what);
     };
     std::vector<std::pair<int, std::vector<double>>> nodeStage;
+    int fmt = 40;  // 22: MSH 2.2, 40: MSH 4.0 (the reference's sample meshes), 41: MSH 4.1 (what current Gmsh writes)
     while (std::getline(in, line)) {
         while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
         if (line == "$MeshFormat") {
@@ -456,8 +457,11 @@ Model readMsh(const std::string& path) {
             double ver;
             int ftype, dsize;
             std::istringstream(line) >> ver >> ftype >> dsize;
-            if (ver < 4.0 || ver >= 4.1 || ftype != 0)
-                throw std::runtime_error("gmshlite: only MSH 4.0 ASCII is supported (got '" + line + "')");
+            if (ftype != 0) throw std::runtime_error("gmshlite: binary MSH files are not supported (got '" + line + "')");
+            if (ver >= 2.0 && ver < 3.0) fmt = 22;
+            else if (ver >= 4.0 && ver < 4.05) fmt = 40;
+            else if (ver >= 4.05 && ver < 4.2) fmt = 41;
+            else throw std::runtime_error("gmshlite: MSH ASCII versions 2.x, 4.0 and 4.1 are supported (got '" + line + "')");
         } else if (line == "$PhysicalNames") {
             expect("PhysicalNames");
             int n = std::stoi(line);
@@ -482,13 +486,49 @@ Model readMsh(const std::string& path) {
                     e.dim = d;
                     double bb;
                     ss >> e.tag;
-                    for (int k = 0; k < 6; ++k) ss >> bb;
+                    for (int k = 0; k < (fmt == 41 && d == 0 ? 3 : 6); ++k) ss >> bb;  // 4.1: points carry X Y Z, the rest a bounding box
                     size_t np = 0;
                     ss >> np;
                     e.phys.resize(np);
                     for (size_t k = 0; k < np; ++k) ss >> e.phys[k];
                     m.entities.push_back(e);
                 }
+        } else if (line == "$Nodes" && fmt == 22) {  // MSH 2.2: numNodes, then "tag x y z"
+            expect("Nodes");
+            const size_t nn = std::stoul(line);
+            for (size_t i = 0; i < nn; ++i) {
+                expect("Nodes");
+                std::istringstream ss(line);
+                int tag;
+                double x, y, z;
+                ss >> tag >> x >> y >> z;
+                if (tag > m.maxNodeTag) m.maxNodeTag = tag;
+                nodeStage.push_back({tag, {x, y, z}});
+            }
+            m.xyz.assign(3 * (size_t)(m.maxNodeTag + 1), 0.0);
+            for (auto& n : nodeStage) std::copy(n.second.begin(), n.second.end(), m.xyz.begin() + 3 * (size_t)n.first);
+        } else if (line == "$Nodes" && fmt == 41) {  // MSH 4.1: per block the node tags first, then the coordinates
+            expect("Nodes");
+            size_t nb, nn;
+            std::istringstream(line) >> nb >> nn;
+            for (size_t b = 0; b < nb; ++b) {
+                expect("Nodes");
+                int ed, et, par;
+                size_t cnt;
+                std::istringstream(line) >> ed >> et >> par >> cnt;
+                std::vector<int> tags(cnt);
+                for (size_t i = 0; i < cnt; ++i) { expect("Nodes"); tags[i] = std::stoi(line); }
+                for (size_t i = 0; i < cnt; ++i) {
+                    expect("Nodes");
+                    std::istringstream ss(line);
+                    double x, y, z;
+                    ss >> x >> y >> z;
+                    if (tags[i] > m.maxNodeTag) m.maxNodeTag = tags[i];
+                    nodeStage.push_back({tags[i], {x, y, z}});
+                }
+            }
+            m.xyz.assign(3 * (size_t)(m.maxNodeTag + 1), 0.0);
+            for (auto& n : nodeStage) std::copy(n.second.begin(), n.second.end(), m.xyz.begin() + 3 * (size_t)n.first);
         } else if (line == "$Nodes") {
             expect("Nodes");
             size_t nb, nn;
@@ -510,6 +550,45 @@ Model readMsh(const std::string& path) {
             }
             m.xyz.assign(3 * (size_t)(m.maxNodeTag + 1), 0.0);
             for (auto& n : nodeStage) std::copy(n.second.begin(), n.second.end(), m.xyz.begin() + 3 * (size_t)n.first);
+        } else if (line == "$Elements" && fmt == 22) {
+            // MSH 2.2: "number type ntags <physical elementary ...> nodes"; no $Entities section: one entity per (dimension,
+            // elementary tag) carrying the physical tag, one block per run of elements of the same entity and type
+            expect("Elements");
+            const size_t ne = std::stoul(line);
+            for (size_t i = 0; i < ne; ++i) {
+                expect("Elements");
+                std::istringstream ss(line);
+                int tag, type, ntags, phys = 0, elem = 0, t;
+                ss >> tag >> type >> ntags;
+                for (int k = 0; k < ntags; ++k) { ss >> t; if (k == 0) phys = t; if (k == 1) elem = t; }
+                int tdim, tord;
+                if (!elementTypeInfo(type, tdim, tord)) {
+                    if (type == 15) continue;  // point elements carry nothing the solver uses
+                    throw std::runtime_error("gmshlite: unsupported element type " + std::to_string(type));
+                }
+                const int nn = refElement(tdim, tord).np;
+                if (m.blocks.empty() || m.blocks.back().entityTag != elem || m.blocks.back().entityDim != tdim || m.blocks.back().type != type) {
+                    ElemBlock blk;
+                    blk.entityTag = elem; blk.entityDim = tdim; blk.type = type;
+                    m.blocks.push_back(std::move(blk));
+                    bool known = false;
+                    for (Entity& e : m.entities)
+                        if (e.dim == tdim && e.tag == elem) {
+                            known = true;
+                            if (phys != 0 && std::find(e.phys.begin(), e.phys.end(), phys) == e.phys.end()) e.phys.push_back(phys);
+                        }
+                    if (!known) {
+                        Entity e;
+                        e.dim = tdim; e.tag = elem;
+                        if (phys != 0) e.phys.push_back(phys);
+                        m.entities.push_back(e);
+                    }
+                }
+                ElemBlock& blk = m.blocks.back();
+                blk.tags.push_back(tag);
+                if (tag > m.maxElemTag) m.maxElemTag = tag;
+                for (int k = 0; k < nn; ++k) { ss >> t; blk.nodeTags.push_back(t); }
+            }
         } else if (line == "$Elements") {
             expect("Elements");
             size_t nb, ne;
@@ -518,7 +597,8 @@ Model readMsh(const std::string& path) {
                 expect("Elements");
                 ElemBlock blk;
                 size_t cnt;
-                std::istringstream(line) >> blk.entityTag >> blk.entityDim >> blk.type >> cnt;
+                if (fmt == 41) std::istringstream(line) >> blk.entityDim >> blk.entityTag >> blk.type >> cnt;  // 4.1 swapped the first two
+                else std::istringstream(line) >> blk.entityTag >> blk.entityDim >> blk.type >> cnt;
                 int tdim, tord;
                 if (!elementTypeInfo(blk.type, tdim, tord))
                     throw std::runtime_error("gmshlite: unsupported element type " + std::to_string(blk.type));

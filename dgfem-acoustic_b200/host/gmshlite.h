@@ -1,5 +1,5 @@
 // gmshlite — a small, self-contained stand-in for the slice of the Gmsh SDK 4.1.4 API that the
-// reference front end uses: MSH 4.0 ASCII reader, equispaced Lagrange simplex
+// reference front end uses: MSH ASCII reader (4.0, 4.1, 2.2), equispaced Lagrange simplex
 // elements of order 1..6 (line / triangle / tetrahedron) in Gmsh's node ordering, exact quadrature of a
 // requested degree, Jacobians with Gmsh's lower-dimensional completion, straight-sided order elevation
 // and a structured Kuhn-tetrahedra cube generator.
@@ -86,7 +86,8 @@ struct Model {
     const double* node(int tag) const { return &xyz[3 * (size_t)tag]; }
 };
 
-// MSH 4.0 ASCII (the only format in doc/**/*.msh, SURVEY.md Appendix D). Throws std::runtime_error.
+// MSH ASCII: 4.0 (the only format in doc/**/*.msh), 4.1 (what current Gmsh writes) and 2.2 (entities are
+// synthesised from the elements' elementary / physical tags). Binary files are rejected. Throws std::runtime_error.
 Model readMsh(const std::string& path);
 // Straight-sided elevation of an order-1 model to `order` (the stand-in for `gmsh -order p`).
 void elevate(Model& m, int order);

@@ -48,7 +48,8 @@ typedef struct dgf_config {
 
 const char* dgf_last_error(void);
 
-/* gmsh::open + (optionally) `gmsh -order p`: order <= 1 keeps the file's order */
+/* gmsh::open + (optionally) `gmsh -order p`: order <= 1 keeps the file's order. MSH ASCII 4.0 (the reference's sample meshes),
+ * 4.1 (current Gmsh) and 2.2 are read; binary files are rejected with an error. */
 dgf_model* dgf_open_msh(const char* path, int order);
 /* synthetic cube of n^3 x 6 Kuhn tetrahedra on [lo,hi]^3 at `order` (BASELINE config 5) */
 dgf_model* dgf_make_cube(int n, double lo, double hi, int order);

@@ -237,3 +237,106 @@ def test_view_writer_round_trip(pkg, mesh_dir, tmp_path):
             np.testing.assert_allclose(vals, U[0] / 343.0 ** 2, rtol=1e-14)
         else:
             np.testing.assert_allclose(vals.reshape(mesh.K, mesh.Np, 3), np.moveaxis(U[1:], 0, -1), rtol=1e-15)
+
+
+def _convert_msh40(text, target):
+    """Rewrites an MSH 4.0 ASCII file (as dgf_write_msh produces it) as MSH 2.2 or MSH 4.1 ASCII."""
+    lines = text.split("\n")
+    sec, cur = {}, None
+    for ln in lines:
+        if ln.startswith("$End"):
+            cur = None
+        elif ln.startswith("$"):
+            cur = ln[1:]
+            sec[cur] = []
+        elif cur:
+            sec[cur].append(ln.strip())
+    phys_names = sec["PhysicalNames"]
+    ents = sec["Entities"]
+    counts = [int(x) for x in ents[0].split()]
+    ent_phys, k = {}, 1
+    for dim in range(4):
+        for _ in range(counts[dim]):
+            t = ents[k].split()
+            k += 1
+            tag, nphys = int(t[0]), int(t[7])
+            ent_phys[(dim, tag)] = [int(x) for x in t[8:8 + nphys]]
+    nodes, i = [], 1
+    nb = int(sec["Nodes"][0].split()[0])
+    node_blocks = []
+    for _ in range(nb):
+        et, ed, par, cnt = (int(x) for x in sec["Nodes"][i].split())
+        blk = [sec["Nodes"][i + 1 + j].split() for j in range(cnt)]
+        node_blocks.append((et, ed, blk))
+        nodes += blk
+        i += 1 + cnt
+    elem_blocks, i = [], 1
+    for _ in range(int(sec["Elements"][0].split()[0])):
+        et, ed, ty, cnt = (int(x) for x in sec["Elements"][i].split())
+        elem_blocks.append((et, ed, ty, [sec["Elements"][i + 1 + j].split() for j in range(cnt)]))
+        i += 1 + cnt
+    out = []
+    if target == 22:
+        out += ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$PhysicalNames"] + phys_names + ["$EndPhysicalNames"]
+        out += ["$Nodes", str(len(nodes))] + [" ".join(n) for n in nodes] + ["$EndNodes"]
+        rows = []
+        for et, ed, ty, els in elem_blocks:
+            ph = ent_phys[(ed, et)][0] if ent_phys[(ed, et)] else 0
+            rows += [f"{e[0]} {ty} 2 {ph} {et} " + " ".join(e[1:]) for e in els]
+        out += ["$Elements", str(len(rows))] + rows + ["$EndElements"]
+    else:
+        out += ["$MeshFormat", "4.1 0 8", "$EndMeshFormat", "$PhysicalNames"] + phys_names + ["$EndPhysicalNames"]
+        out += ["$Entities", ents[0]]
+        k = 1
+        for dim in range(4):
+            for _ in range(counts[dim]):
+                t = ents[k].split()
+                k += 1
+                nphys = int(t[7])
+                head = [t[0]] + (t[1:4] if dim == 0 else t[1:7])
+                out.append(" ".join(head + [str(nphys)] + t[8:8 + nphys] + ([] if dim == 0 else ["0"])))
+        out.append("$EndEntities")
+        tags = [int(n[0]) for n in nodes]
+        out += ["$Nodes", f"{len(node_blocks)} {len(nodes)} {min(tags)} {max(tags)}"]
+        for et, ed, blk in node_blocks:
+            out.append(f"{ed} {et} 0 {len(blk)}")
+            out += [n[0] for n in blk] + [" ".join(n[1:]) for n in blk]
+        out.append("$EndNodes")
+        etags = [int(e[0]) for b in elem_blocks for e in b[3]]
+        out += ["$Elements", f"{len(elem_blocks)} {len(etags)} {min(etags)} {max(etags)}"]
+        for et, ed, ty, els in elem_blocks:
+            out.append(f"{ed} {et} {ty} {len(els)}")
+            out += [" ".join(e) for e in els]
+        out.append("$EndElements")
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("target", [22, 41])
+@pytest.mark.parametrize("source", ["cube", "square.msh"])
+def test_msh_22_and_41_readers_give_the_same_mesh_as_40(pkg, mesh_dir, tmp_path, source, target):
+    """Current Gmsh writes MSH 4.1 and many meshes in the wild are MSH 2.2; the reference (Gmsh SDK) opens all of them. The
+    stand-in reads the ASCII variants of the three; the same mesh in each gives the same Mesh arrays and boundary tags."""
+    if source == "cube":
+        base = tmp_path / "m40.msh"
+        pkg.Model.make_cube(2, -1.0, 1.0, 1).write_msh(base)
+        bc_name = "Boundary"
+    else:
+        base = mesh_dir / source
+        bc_name = "Absorbing"
+    other = tmp_path / f"m{target}.msh"
+    other.write_text(_convert_msh40(base.read_text(), target))
+    conf = tmp_path / "c.conf"
+    conf.write_text(f"timeStart=0\ntimeEnd=1\ntimeStep=0.1\ntimeRate=0.5\nelementType=Lagrange\ntimeIntMethod=Runge-Kutta\nsaveFile=o\nnumThreads=1\n"
+                    f"v0_x=0\nv0_y=0\nv0_z=0\nrho0=1\nc0=1\n{bc_name} = Reflecting\n")
+    meshes = []
+    for path in (base, other):
+        model = pkg.Model.open_msh(path, 2)
+        cfg = model.parse_config(conf)
+        assert cfg.c.nPhysBC == 1
+        meshes.append(pkg.Mesh(model, cfg))
+    a, b = meshes
+    assert (a.K, a.F, a.Np) == (b.K, b.F, b.Np)
+    assert np.array_equal(a.node_coords, b.node_coords) and np.array_equal(a.el_tags, b.el_tags)
+    for name in ("elFId", "elFOrientation", "fNbrElId", "fNToElNId", "fIsBoundary", "fBC"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert np.array_equal(a.fNormal, b.fNormal) and (a.fBC[a.fIsBoundary == 1] == 1).all()
