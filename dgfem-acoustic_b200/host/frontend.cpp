@@ -42,6 +42,7 @@ extern "C" dgf_model* dgf_open_msh(const char* path, int order) {
         auto* mm = new dgf_model;
         mm->m = gml::readMsh(path);
         if (order > 1) gml::elevate(mm->m, order);
+        else gml::detectCurved(mm->m);  // a high-order file of a curved geometry: per-integration-point geometry downstream
         return mm;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -880,6 +880,31 @@ void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const 
     completeJacobian(dim, jac, det);
 }
 
+bool detectCurved(Model& m) {
+    for (const ElemBlock& blk : m.blocks) {
+        int dim, order;
+        if (!elementTypeInfo(blk.type, dim, order) || order < 2 || dim < 1) continue;
+        const RefElement& re = refElement(dim, order);
+        const RefElement& lin = refElement(dim, 1);
+        std::vector<double> phi(lin.np);
+        for (size_t e = 0; e < blk.tags.size(); ++e) {
+            const int* nt = &blk.nodeTags[e * re.np];
+            double scale = 0;
+            for (int v = 1; v < lin.np; ++v)
+                for (int x = 0; x < 3; ++x) scale = std::max(scale, std::fabs(m.node(nt[v])[x] - m.node(nt[0])[x]));
+            for (int n = lin.np; n < re.np; ++n) {
+                lin.basis(&re.uvw[3 * n], phi.data());
+                for (int x = 0; x < 3; ++x) {
+                    double sx = 0;
+                    for (int v = 0; v < lin.np; ++v) sx += phi[v] * m.node(nt[v])[x];
+                    if (std::fabs(sx - m.node(nt[n])[x]) > 1e-10 * scale) { m.curved = true; return true; }
+                }
+            }
+        }
+    }
+    return m.curved;
+}
+
 static void warpImpl(Model& m, double amp, double k, const double* center, double radius) {
     const int dim = m.dimension();
     for (int tag = 0; tag <= m.maxNodeTag; ++tag) {

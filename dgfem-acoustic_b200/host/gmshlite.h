@@ -106,6 +106,9 @@ void isoJacobian(const Model& m, int dim, int order, const int* nodeTags, const 
 // dimension (2D models stay in their plane): turns a straight-sided order-p mesh into a conforming curved isoparametric one
 // (the stand-in for meshing a curved geometry with `gmsh -order p`). Sets Model::curved.
 void warp(Model& m, double amp, double k);
+// Sets Model::curved if some high-order node of some element is not where the affine map of the element's vertices puts it
+// (a mesh file written by `gmsh -order p` on a curved geometry); returns the flag.
+bool detectCurved(Model& m);
 // The same displacement multiplied by the window (1 - (r/R)^2)^2 around `center` (zero for r >= R): only the elements that
 // reach into the ball become curved, the rest of the mesh stays exactly straight-sided (a curved layer in a straight mesh).
 void warpLocal(Model& m, double amp, double k, const double center[3], double radius);

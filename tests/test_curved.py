@@ -139,3 +139,21 @@ def test_engine_on_curved_meshes(pkg, oracle_mod, mesh_dir, name, order, v0, war
     with pytest.raises(pkg.DgbError):
         eng.set_option("kernel", 4)  # no Bernstein representation next to curved elements
     eng.close()
+
+
+def test_a_high_order_file_of_a_curved_mesh_is_recognised(pkg, mesh_dir, tmp_path):
+    """What `gmsh -order p` writes for a curved geometry: high-order elements whose extra nodes are off the straight-sided
+    positions. Written here from a warped model, read back: same geometry, curved layout; a straight-sided high-order file stays
+    in the compressed affine layout."""
+    model = pkg.Model.make_cube(2, -10.0, 10.0, 3).warp(0.4, 0.3)
+    a = pkg.Mesh(model, pkg.Config())
+    path = tmp_path / "curved_p3.msh"
+    model.write_msh(path)
+    b = pkg.Mesh(pkg.Model.open_msh(path, 1), pkg.Config())  # order <= 1: keep the file's order
+    assert (b.order, b.K) == (3, a.K) and b.desc.nGeomEl == b.desc.nG and b.desc.nGeomF == b.desc.nGf
+    assert np.array_equal(a.node_coords, b.node_coords) and np.array_equal(a.elJacobianDet, b.elJacobianDet)
+    assert np.array_equal(a.fNormal, b.fNormal)
+    straight = tmp_path / "straight_p3.msh"
+    pkg.Model.make_cube(2, -10.0, 10.0, 3).write_msh(straight)
+    c = pkg.Mesh(pkg.Model.open_msh(straight, 1), pkg.Config())
+    assert c.order == 3 and c.desc.nGeomEl == 1 and c.desc.nGeomF == 1
