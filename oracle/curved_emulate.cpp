@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../dgfem-acoustic_b200/csrc/stage_curved.cu"
+#include "../dgfem-acoustic_b200/csrc/stage_generic.cu"  // the collapsed kernel of the straight-sided prefix of a mixed handle
+#include "emu_layout.h"
 
 using namespace dgb;
 
@@ -91,6 +93,45 @@ int cve_run(const dgb_desc* d, int integrator, double* u, int nsteps) {
         }
         std::copy(pU, pU + n, u);
         return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// A mixed handle as dgb_run drives it (launchStage in csrc/dgb_api.cu): per stage the collapsed generic kernel on the
+// straight-sided prefix [0, first) and the curved kernel on the suffix [first, K), both updating the same RK registers.
+int cve_run_mixed(const dgb_desc* d, int integrator, double* u, int nsteps) {
+    try {
+        const std::vector<uint8_t> flag = curvedElements(d);
+        const int first = curvedSuffixStart(flag);
+        const std::vector<double> Minv = curvedInverseMass(d, first);
+        const CurvedMesh C = fromDesc(d, Minv, first);
+        emu::Layout L;
+        emu::build(d, L);
+        const StageKernel k = selectGenericKernel(d->dim, d->order);
+        const size_t n = (size_t)4 * d->K * d->Np;
+        std::vector<double> U(u, u + n), ACC(n, 0.0), YA(n, 0.0), YB(n, 0.0);
+        double *pU = U.data(), *pYA = YA.data(), *pYB = YB.data();
+        StageArgs A{};
+        A.acc = ACC.data(); A.dt = d->dt;
+        auto stage = [&](const double* yin, double* yout, int mode) {
+            A.yin = yin; A.yout = yout; A.mode = mode; A.u = pU;
+            StageArgs B = A;
+            B.eBegin = 0; B.eEnd = first;
+            if (first > 0) k.launch(L.M, B, nullptr);
+            B.eBegin = first; B.eEnd = d->K;
+            launchCurved(C, B, nullptr);
+        };
+        for (int step = 0; step < nsteps; ++step) {
+            if (integrator == 0) { stage(pU, pYA, MODE_EULER); std::swap(pU, pYA); continue; }
+            stage(pU, pYA, MODE_RK1);
+            stage(pYA, pYB, MODE_RK2);
+            stage(pYB, pYA, MODE_RK3);
+            stage(pYA, nullptr, MODE_RK4);
+        }
+        std::copy(pU, pU + n, u);
+        return first;
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1;

@@ -23,6 +23,7 @@ def cve():
     lib.cve_is_curved.argtypes = [C.c_void_p]
     lib.cve_first_curved.argtypes = [C.c_void_p]
     lib.cve_rhs_suffix.argtypes = [C.c_void_p, C.c_int, dp]
+    lib.cve_run_mixed.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
     return lib
 
 
@@ -106,6 +107,22 @@ def test_curved_patch_in_a_straight_mesh(pkg, oracle_mod, cve, mesh_dir, name, o
         op = op.reshape(4, mesh.K, mesh.Np)
         for q in range(4):
             assert rel_l2(op[q, :first], ref[q, :first]) < 1e-12
+
+
+@pytest.mark.parametrize("name,order,v0,warp", MIXED)
+def test_emulated_mixed_handle_equals_the_faithful_oracle(pkg, oracle_mod, cve, mesh_dir, name, order, v0, warp):
+    """Time marching of a mixed handle the way dgb_run drives it: two launches per stage on disjoint element ranges (the collapsed
+    generic kernel on the straight-sided prefix, the curved kernel on the suffix) sharing the RK registers; RK4 and Euler."""
+    mesh, u = _case(pkg, mesh_dir, name, order, v0, warp)
+    d = C.cast(mesh.desc_p, C.c_void_p)
+    for integrator, ident in ((1, pkg.RUNGE_KUTTA), (0, pkg.EULER1)):
+        got = u.copy()
+        first = cve.cve_run_mixed(d, integrator, got.ctypes.data_as(dp), 3)
+        assert 0 < first < mesh.K, cve.cve_last_error()
+        want = u.copy()
+        oracle_mod.Oracle(mesh).run(oracle_mod.Oracle.FAITHFUL, ident, want, 0.0, 3)
+        for q in range(4 if mesh.dim == 3 else 3):
+            assert rel_l2(got[q], want[q]) < 1e-12
 
 
 def test_straight_sided_meshes_are_not_flagged(pkg, cve, mesh_dir):
