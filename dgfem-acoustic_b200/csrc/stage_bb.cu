@@ -5,7 +5,7 @@
 // dgb_get_state convert with V^-1 / V). In that basis the reference's dense per-element operators — the stiffness
 // quadrature of Mesh::getElStiffVector (Mesh.cpp:476-489), the inverse mass of eigen::linEq (utils.cpp:118-123) and the
 // face integrals of Mesh::precomputeFlux / getElFlux (Mesh.cpp:500-557) — collapse to the sparse closed forms of
-// bb_ops.h: ~6 kFLOP per element and stage at order 4 instead of ~36 k for the dense contractions, which moves the
+// bb_ops.h: ~6.6 k FP64 instructions per element and stage at order 4 instead of ~36 kFLOP of dense contractions, which moves the
 // order-4 stage from the FP64 roof to the HBM roof. CUDA cores only: there is nothing dense left.
 //
 // One CTA takes TE consecutive elements:
