@@ -10,6 +10,7 @@
 // done: the array a rank pushes into at stage s+1 was last read by the peer at a stage <= s, and the sender's stage
 // s+1 cannot start before the peer has pushed (hence finished) its stage s (the neighbour relation is symmetric).
 #include "dgb_internal.h"
+#include "dgb_launch.h"  // the CPU tests run this file under oracle/cuda_emu.h (DGB_EMULATE)
 
 namespace dgb {
 namespace {
@@ -29,8 +30,12 @@ __global__ void pushHaloKernel(const double* __restrict__ y, int64_t stride, int
 __global__ void signalPeersKernel(PeerFlags F, unsigned long long epoch) {
     const int i = threadIdx.x;
     if (i < F.n) {
+#ifdef DGB_EMULATE
+        __atomic_store_n(F.flag[i], epoch, __ATOMIC_RELEASE);
+#else
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.flag[i]), "l"(epoch) : "memory");
+#endif
     }
 }
 
@@ -40,6 +45,9 @@ __global__ void waitPeersKernel(const unsigned long long* flags, PeerWait W, uns
     const int i = threadIdx.x;
     if (i < W.n) {
         const unsigned long long* f = flags + W.rank[i];
+#ifdef DGB_EMULATE
+        if (__atomic_load_n(f, __ATOMIC_ACQUIRE) < epoch) *err = 1 + W.rank[i];  // the emulation runs the ranks one after the other: no spinning
+#else
         unsigned long long t0, t1, v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (;;) {
@@ -53,6 +61,7 @@ __global__ void waitPeersKernel(const unsigned long long* flags, PeerWait W, uns
             }
             __nanosleep(200);
         }
+#endif
     }
 }
 
@@ -63,16 +72,16 @@ void launchPushHalo(const double* y, int64_t stride, int Np, const int32_t* send
     const int64_t tot = 4ll * nSend * Np;
     if (tot <= 0) return;
     const unsigned blocks = (unsigned)std::min<int64_t>((tot + 255) / 256, 148 * 8);
-    pushHaloKernel<<<blocks, 256, 0, s>>>(y, stride, Np, sendElems, sendPeer, sendSlot, nSend, T);
+    DGB_LAUNCH(pushHaloKernel, blocks, 256, 0, s, y, stride, Np, sendElems, sendPeer, sendSlot, nSend, T);
 }
 
 void launchSignalPeers(const PeerFlags& F, unsigned long long epoch, cudaStream_t s) {
-    if (F.n > 0) signalPeersKernel<<<1, 32, 0, s>>>(F, epoch);
+    if (F.n > 0) DGB_LAUNCH(signalPeersKernel, 1, 32, 0, s, F, epoch);
 }
 
 void launchWaitPeers(const unsigned long long* flags, const PeerWait& W, unsigned long long epoch, unsigned long long timeoutNs, int* err,
                      cudaStream_t s) {
-    if (W.n > 0) waitPeersKernel<<<1, 32, 0, s>>>(flags, W, epoch, timeoutNs, err);
+    if (W.n > 0) DGB_LAUNCH(waitPeersKernel, 1, 32, 0, s, flags, W, epoch, timeoutNs, err);
 }
 
 }  // namespace dgb
