@@ -16,6 +16,7 @@
 #include "bb_setup.h"
 #include "curved_setup.h"
 #include "dgb_internal.h"
+#include "dgb_launch.h"
 #include "partition.h"
 #include "tile_cfg.h"
 
@@ -124,6 +125,7 @@ struct dgb_handle {
     DeviceMesh M{};
     dgb_desc hd{};  // scalar members of the global desc
     int Kglobal = 0, Np = 0;
+    int device = 0;  // the CUDA device the handle was created on; every entry point makes it current
     bool partitioned = false;
     int nranks = 1;
     PartitionPlan plan;
@@ -161,6 +163,7 @@ struct dgb_handle {
     cudaGraphExec_t stepGraph = nullptr;
     double stepGraphDt = 0;
     StageLaunchFn stepGraphKernel = nullptr;
+    const double* stepGraphPtr[3] = {nullptr, nullptr, nullptr};  // U / YA / YB the graph was captured with (Euler runs swap the names)
     int timeStages = 1;
     // sources
     std::vector<int32_t> srcOff;
@@ -206,12 +209,23 @@ struct dgb_handle {
 
 namespace {
 
+// Makes the handle's device current for the duration of an API call (a process may hold handles on several GPUs).
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(const dgb_handle* h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device && cudaSetDevice(h->device) == cudaSuccess) prev = cur;
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 void freeHandle(dgb_handle* h) {
     if (!h) return;
+    DeviceScope onDevice(h);
     auto F = [](void* p) { if (p) cudaFree(p); };
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
-    if (h->comm) nccl().CommDestroy(h->comm);
     if (h->stepGraph) cudaGraphExecDestroy(h->stepGraph);
     if (h->hostStage) cudaFreeHost(h->hostStage);
     if (h->snapStream) { cudaStreamSynchronize(h->snapStream); cudaStreamDestroy(h->snapStream); }
@@ -219,10 +233,14 @@ void freeHandle(dgb_handle* h) {
     F(h->dSnap);
     for (auto& pm : h->peerMap) if (pm.opened) cudaIpcCloseMemHandle(pm.opened);
     if (h->arena && h->comm && h->stream) {
-        // peers still map this rank's arena: every rank closes its mappings (above) before anybody frees (collective destroy)
+        // peers still map this rank's arena: every rank closes its mappings (above) before anybody frees (collective destroy).
+        // The communicator must still be alive here: it is destroyed only after this barrier.
         char* scratch = h->arena + h->arenaFlagOffset + 128;  // the second half of the flag block is unused
-        if (nccl().AllGather(scratch + h->plan.rank, scratch, 1, ncclChar, h->comm, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
+        const ncclResult_t r = nccl().AllGather(scratch + h->plan.rank, scratch, 1, ncclChar, h->comm, h->stream);
+        if (r == ncclSuccess) cudaStreamSynchronize(h->stream);
+        else fprintf(stderr, "dgb_destroy: arena barrier failed (%s); a peer may still map this rank's arena\n", nccl().GetErrorString(r));
     }
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
     for (void* p : h->curvedAllocs) F(p);
@@ -347,6 +365,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
     try {
         const int Np = d->Np, Nfp = d->Nfp, Nf = d->Nf, dim = d->dim, K = d->K;
         h->hd = *d;
+        CUDA_CHECK(cudaGetDevice(&h->device));
         h->Kglobal = K;
         h->Np = Np;
         h->partitioned = nranks > 1;
@@ -860,7 +879,8 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
         stages(true);  // step 0, eager (and timed: dgb_last_stage_kernel_ms)
         t += dt;
         step0 = 1;
-        if (!h->stepGraph || h->stepGraphDt != dt || h->stepGraphKernel != h->active.launch) {
+        if (!h->stepGraph || h->stepGraphDt != dt || h->stepGraphKernel != h->active.launch || h->stepGraphPtr[0] != h->U ||
+            h->stepGraphPtr[1] != h->YA || h->stepGraphPtr[2] != h->YB) {
             if (h->stepGraph) { cudaGraphExecDestroy(h->stepGraph); h->stepGraph = nullptr; }
             cudaGraph_t graph = nullptr;
             const int64_t launchesBefore = h->launches;
@@ -872,6 +892,7 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
             cudaGraphDestroy(graph);
             h->stepGraphDt = dt;
             h->stepGraphKernel = h->active.launch;
+            h->stepGraphPtr[0] = h->U; h->stepGraphPtr[1] = h->YA; h->stepGraphPtr[2] = h->YB;
         }
         for (int step = step0; step < nsteps; ++step, t += dt) {
             CUDA_CHECK(cudaGraphLaunch(h->stepGraph, h->stream));
@@ -944,6 +965,9 @@ int guarded(Fn fn) {
     } catch (const DgbException& e) {
         g_err = e.what();
         return e.code;
+    } catch (const UnsupportedError& e) {
+        g_err = e.what();
+        return DGB_ERR_UNSUPPORTED;
     } catch (const std::exception& e) {
         g_err = e.what();
         return DGB_ERR_ARG;
@@ -1066,6 +1090,7 @@ void dgb_destroy(dgb_handle* h) { freeHandle(h); }
 
 int dgb_set_state(dgb_handle* h, const double* u) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !u) throw DgbException(DGB_ERR_ARG, "null argument");
         stateToDevice(h, u, h->U);
         h->stateSet = true;
@@ -1074,6 +1099,7 @@ int dgb_set_state(dgb_handle* h, const double* u) {
 
 int dgb_get_state(dgb_handle* h, double* u) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !u) throw DgbException(DGB_ERR_ARG, "null argument");
         if (!h->stateSet) throw DgbException(DGB_ERR_STATE, "dgb_get_state before dgb_set_state");
         stateToHost(h, h->U, u);
@@ -1082,6 +1108,7 @@ int dgb_get_state(dgb_handle* h, double* u) {
 
 int dgb_snapshot_begin(dgb_handle* h, double* u_host) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !u_host) throw DgbException(DGB_ERR_ARG, "null argument");
         if (!h->stateSet) throw DgbException(DGB_ERR_STATE, "dgb_snapshot_begin before dgb_set_state");
         if (h->partitioned) throw DgbException(DGB_ERR_UNSUPPORTED, "asynchronous snapshots are not available on partitioned handles");
@@ -1105,6 +1132,7 @@ int dgb_snapshot_begin(dgb_handle* h, double* u_host) {
 
 int dgb_snapshot_end(dgb_handle* h) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
         if (!h->snapPending) throw DgbException(DGB_ERR_STATE, "dgb_snapshot_end without dgb_snapshot_begin");
         CUDA_CHECK(cudaEventSynchronize(h->evSnapDone));
@@ -1122,6 +1150,7 @@ void dgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32_t* nodeIdx, const double* amp, const double* freq,
                     const double* phase, const double* duration) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || nsrc < 0 || (nsrc > 0 && (!offsets || !amp || !freq || !phase || !duration))) throw DgbException(DGB_ERR_ARG, "bad source arguments");
         std::vector<int32_t> off(1, 0), idx;
         for (int s = 0; s < nsrc; ++s) {
@@ -1167,6 +1196,7 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
 
 int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || nprobe < 0 || (nprobe > 0 && !nodeIdx)) throw DgbException(DGB_ERR_ARG, "bad probe arguments");
         std::vector<int32_t> idx(nprobe);
         for (int j = 0; j < nprobe; ++j) idx[j] = localNode(h, nodeIdx[j], false);
@@ -1192,8 +1222,13 @@ int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
 
 int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !nsteps) throw DgbException(DGB_ERR_ARG, "null argument");
-        const int n = std::min(h->probeCount, capacity_steps);
+        if (capacity_steps < h->probeCount) {  // nothing is dropped: the record stays until a large enough buffer reads it
+            *nsteps = h->probeCount;
+            throw DgbException(DGB_ERR_ARG, "dgb_get_probes: capacity_steps " + std::to_string(capacity_steps) + " < recorded steps " + std::to_string(h->probeCount));
+        }
+        const int n = h->probeCount;
         if (n > 0 && h->nprobe > 0) {
             if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
             CUDA_CHECK(cudaMemcpyAsync(out, h->dProbeRec, (size_t)n * h->nprobe * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1206,6 +1241,7 @@ int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps) 
 
 int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || nrecv < 0 || (nrecv > 0 && (!el || !weights))) throw DgbException(DGB_ERR_ARG, "bad receiver arguments");
         std::vector<int32_t> loc(nrecv);
         for (int j = 0; j < nrecv; ++j) {
@@ -1235,8 +1271,13 @@ int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double*
 
 int dgb_get_receivers(dgb_handle* h, double* out, int capacity_steps, int* nsteps) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !nsteps) throw DgbException(DGB_ERR_ARG, "null argument");
-        const int n = std::min(h->recvCount, capacity_steps);
+        if (capacity_steps < h->recvCount) {
+            *nsteps = h->recvCount;
+            throw DgbException(DGB_ERR_ARG, "dgb_get_receivers: capacity_steps " + std::to_string(capacity_steps) + " < recorded steps " + std::to_string(h->recvCount));
+        }
+        const int n = h->recvCount;
         if (n > 0 && h->nrecv > 0) {
             if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
             CUDA_CHECK(cudaMemcpyAsync(out, h->dRecvRec, (size_t)n * h->nrecv * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1248,11 +1289,12 @@ int dgb_get_receivers(dgb_handle* h, double* out, int capacity_steps, int* nstep
 }
 
 int dgb_run(dgb_handle* h, int integrator, double t_start, int nsteps, double* t_end) {
-    return guarded([&] { runImpl(h, integrator, t_start, nsteps, t_end); });
+    return guarded([&] { DeviceScope onDevice(h); runImpl(h, integrator, t_start, nsteps, t_end); });
 }
 
 int dgb_eval_rhs(dgb_handle* h, const double* u, double* rhs) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !u || !rhs) throw DgbException(DGB_ERR_ARG, "null argument");
         stateToDevice(h, u, h->YA);
         StageArgs A{};
@@ -1266,6 +1308,7 @@ int dgb_eval_rhs(dgb_handle* h, const double* u, double* rhs) {
 
 int dgb_set_stream(dgb_handle* h, void* cuda_stream) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
@@ -1276,6 +1319,7 @@ int dgb_set_stream(dgb_handle* h, void* cuda_stream) {
 
 int dgb_synchronize(dgb_handle* h) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h) throw DgbException(DGB_ERR_ARG, "handle is null");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         if (h->commStream) CUDA_CHECK(cudaStreamSynchronize(h->commStream));
@@ -1289,6 +1333,7 @@ const char* dgb_kernel_name(dgb_handle* h) { return !h ? "none" : h->curved ? h-
 
 int dgb_set_option(dgb_handle* h, const char* key, int value) {
     return guarded([&] {
+        DeviceScope onDevice(h);
         if (!h || !key) throw DgbException(DGB_ERR_ARG, "null argument");
         const std::string k(key);
         if (k == "kernel") {

@@ -365,11 +365,8 @@ void launchBBSeq(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
 #ifndef DGB_EMULATE
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(stageBBSeqKernel<P, TE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        configured = true;
-    }
+    static KernelConfig kc;
+    configureKernel(kc, stageBBSeqKernel<P, TE_>, C::SMEM, "stage_bb_seq");
 #endif
     DGB_LAUNCH((stageBBSeqKernel<P, TE_>), (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }
@@ -380,11 +377,8 @@ void launchBB(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
 #ifndef DGB_EMULATE
-    static bool configured = false;  // one device per process
-    if (!configured) {
-        cudaFuncSetAttribute(stageBBKernel<P, TE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        configured = true;
-    }
+    static KernelConfig kc;
+    configureKernel(kc, stageBBKernel<P, TE_>, C::SMEM, "stage_bb");
 #endif
     DGB_LAUNCH((stageBBKernel<P, TE_>), (nEl + C::TE - 1) / C::TE, C::THREADS, C::SMEM, s, M, A);
 }

@@ -191,11 +191,8 @@ void launchCurved(const CurvedMesh& C, const StageArgs& A, cudaStream_t s) {
     if (nEl <= 0) return;
     const size_t bytes = curvedSmemBytes(C);
 #ifndef DGB_EMULATE
-    static size_t configured = 0;
-    if (bytes > configured) {
-        cudaFuncSetAttribute(stageCurvedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        configured = bytes;
-    }
+    static KernelConfig kc;
+    configureKernel(kc, stageCurvedKernel, bytes, "stage_curved");
 #endif
     DGB_LAUNCH(stageCurvedKernel, nEl, CURVED_THREADS, bytes, s, C, A);
 }

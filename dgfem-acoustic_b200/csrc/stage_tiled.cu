@@ -23,6 +23,7 @@
 
 #include "dgb_device.cuh"
 #include "dgb_internal.h"
+#include "dgb_launch.h"
 #include "tile_cfg.h"
 
 namespace dgb {
@@ -540,16 +541,9 @@ void launchTiledImpl(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using T = TetTile<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
-    static int numSm = 0;
-    static bool configured = false;
+    static KernelConfig kc;
     const size_t smem = (size_t)(T::OPS + kWarps * WarpLayout<P>::DOUBLES) * sizeof(double) + T::NFL * sizeof(int) + kMaxMaps * T::NFP;
-    if (!configured) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(stageTiledKernel<P, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    const int numSm = configureKernel(kc, stageTiledKernel<P, FLOW>, smem, "stage_tiled_dmma");
     const int nUnits = (nEl + 3) / 4;
     const int grid = std::max(1, std::min(numSm - std::min(A.smReserve, numSm / 2), (nUnits + kWarps - 1) / kWarps));
     stageTiledKernel<P, FLOW><<<grid, kWarps * 32, smem, s>>>(M, A, nUnits);

@@ -33,6 +33,7 @@
 
 #include "dgb_device.cuh"
 #include "dgb_internal.h"
+#include "dgb_launch.h"
 
 namespace dgb {
 
@@ -725,17 +726,10 @@ void launchWs(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = WsCfg<P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
-    static int numSm = 0;
-    static bool configured = false;
+    static KernelConfig kc;
     static_assert(kNumBars <= 32, "barrier block");
     const size_t smem = C::SMEM_BYTES;
-    if (!configured) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(stageWsKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    const int numSm = configureKernel(kc, stageWsKernel<P>, smem, "stage_ws_dmma");
     const int nTiles = (nEl + kTileEl - 1) / kTileEl;
     const int grid = std::max(1, std::min(numSm - std::min(A.smReserve, numSm / 2), nTiles));
     stageWsKernel<P><<<grid, kThreadsWs, smem, s>>>(M, A, nTiles);

@@ -49,7 +49,10 @@ int main(int argc, char** argv) {
             amp.push_back(cfg.sources[s][5]); freq.push_back(cfg.sources[s][6]);
             phase.push_back(cfg.sources[s][7]); dur.push_back(cfg.sources[s][8]);
         }
-        dgb_set_sources(h, cfg.nSources, off.data(), idx.data(), amp.data(), freq.data(), phase.data(), dur.data());
+        if (dgb_set_sources(h, cfg.nSources, off.data(), idx.data(), amp.data(), freq.data(), phase.data(), dur.data()) != DGB_OK) {
+            std::fprintf(stderr, "Error   : %s\n", dgb_last_error());
+            return EXIT_FAILURE;
+        }
     }
     // receivers (keys `receiver<name> = x, y, z`, ignored by the reference's parser): located once, sampled on the device
     std::vector<double> rcvRec;
@@ -65,12 +68,13 @@ int main(int argc, char** argv) {
         if (dgb_set_receivers(h, cfg.nReceivers, rEl.data(), rW.data()) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
     }
     auto drainReceivers = [&](int nsteps) {
-        if (cfg.nReceivers == 0 || nsteps == 0) return;
+        if (cfg.nReceivers == 0 || nsteps == 0) return true;
         const size_t at = rcvRec.size();
         rcvRec.resize(at + (size_t)nsteps * cfg.nReceivers * 4);
         int got = 0;
-        dgb_get_receivers(h, rcvRec.data() + at, nsteps, &got);
+        if (dgb_get_receivers(h, rcvRec.data() + at, nsteps, &got) != DGB_OK) { rcvRec.resize(at); return false; }
         rcvRec.resize(at + (size_t)got * cfg.nReceivers * 4);
+        return true;
     };
     if (dgb_set_state(h, u.data()) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
 
@@ -103,7 +107,7 @@ int main(int argc, char** argv) {
                 if (!ok || dgb_get_state(h, u.data()) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
                 snapU.insert(snapU.end(), u.begin(), u.end());
             }
-            drainReceivers(pending);
+            if (!drainReceivers(pending)) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
             pending = 0;
             tPending = t;
             snapStep.push_back((int32_t)step);
@@ -113,9 +117,8 @@ int main(int argc, char** argv) {
         }
         ++pending;
     }
-    dgb_run(h, integrator, tPending, pending, nullptr);
-    if (!collect()) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
-    drainReceivers(pending);
+    if (dgb_run(h, integrator, tPending, pending, nullptr) != DGB_OK) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
+    if (!collect() || !drainReceivers(pending)) { std::fprintf(stderr, "Error   : %s\n", dgb_last_error()); return EXIT_FAILURE; }
     if (cfg.nReceivers > 0) {
         const int nrec = (int)(rcvRec.size() / ((size_t)cfg.nReceivers * 4));
         if (dgf_write_receivers(cfg.receiverFile, cfg.nReceivers, &cfg.receivers[0][0], nrec, cfg.timeStart, cfg.timeStep, rcvRec.data()) != 0)
@@ -127,11 +130,12 @@ int main(int argc, char** argv) {
         }
     }
     std::printf("Info    : %lld kernel launches, last chunk %.3f ms on the device\n", (long long)dgb_launch_count(h), dgb_last_run_ms(h));
-    dgf_write_views(cfg.saveFile, model, mesh, &cfg, (int)snapStep.size(), snapStep.data(), snapTime.data(), snapU.data());
+    const int viewsRc = dgf_write_views(cfg.saveFile, model, mesh, &cfg, (int)snapStep.size(), snapStep.data(), snapTime.data(), snapU.data());
+    if (viewsRc != 0) std::fprintf(stderr, "Error   : %s\n", dgf_last_error());
     dgb_destroy(h);
     dgb_host_free(pinned[0]);
     dgb_host_free(pinned[1]);
     dgf_mesh_free(mesh);
     dgf_model_free(model);
-    return EXIT_SUCCESS;
+    return viewsRc == 0 ? EXIT_SUCCESS : EXIT_FAILURE;
 }

@@ -124,7 +124,8 @@ int dgb_set_sources(dgb_handle* h, int nsrc, const int32_t* offsets, const int32
  * reference's snapshots, src/solver.cpp:222-238). */
 int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx);
 /* out[step][probe][4]; returns the number of recorded steps in *nsteps and clears the record. Probes owned
- * by another rank are returned as 0. */
+ * by another rank are returned as 0. If capacity_steps is smaller than the number of recorded steps nothing is
+ * copied or cleared: the call returns DGB_ERR_ARG with the required capacity in *nsteps. */
 int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps);
 
 /* Receivers (new capability): receiver j records the four fields interpolated at a point inside
@@ -132,7 +133,8 @@ int dgb_get_probes(dgb_handle* h, double* out, int capacity_steps, int* nsteps);
  * the point (dgf_locate_point in include/dgfront.h computes both), at the START of every step like the probes.
  * el uses global element ids; receivers whose element another rank owns are returned as 0. */
 int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double* weights /* [nrecv][Np] */);
-/* out[step][receiver][4]; returns the number of recorded steps in *nsteps and clears the record. */
+/* out[step][receiver][4]; returns the number of recorded steps in *nsteps and clears the record; a too small
+ * capacity_steps is refused like in dgb_get_probes. */
 int dgb_get_receivers(dgb_handle* h, double* out, int capacity_steps, int* nsteps);
 
 /* ---- time marching ----------------------------------------------------------------------------------- */

@@ -132,7 +132,6 @@ def test_straight_sided_meshes_are_not_flagged(pkg, cve, mesh_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("DGB_TEST_CURVED") != "1", reason="curved-element kernel not yet run on hardware: set DGB_TEST_CURVED=1")
 @pytest.mark.parametrize("name,order,v0,warp", CASES + [("disk.msh", 3, (0.0, 0.0, 0.0), (0.05, 1.5))] + MIXED +
                          [("cube:6", 4, (0.0, 0.0, 0.0), (0.4, 0.3, (0.0, 0.0, 0.0), 6.0))])
 def test_engine_on_curved_meshes(pkg, oracle_mod, mesh_dir, name, order, v0, warp):

@@ -1,17 +1,14 @@
 """Bernstein-Bezier stage kernel (csrc/stage_bb.cu, dgb_set_option("kernel", 4)) against the CPU oracle, through the C ABI.
 
-The operator code of this kernel is checked on the CPU (tests/test_bb_ops.py runs the same templates on the host); the
-kernel around it was written after this round's GPU budget was spent and has not run on hardware yet, so the file is
-gated: DGB_TEST_BB=1 enables it (first thing to run next round, profiles/run_unverified.sh). Tolerance 1e-10 as everywhere."""
-import os
+The operator code of this kernel is also checked on the CPU (tests/test_bb_ops.py runs the same templates on the host,
+tests/test_bb_emulated.py the kernel source through a CUDA emulation). Tolerance 1e-10 as everywhere."""
 
 import numpy as np
 import pytest
 
 from conftest import rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DGB_TEST_BB") != "1", reason="Bernstein-Bezier kernel not yet run on hardware: set DGB_TEST_BB=1")]
+pytestmark = [pytest.mark.gpu]
 TOL = 1e-10
 
 

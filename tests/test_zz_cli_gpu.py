@@ -1,7 +1,7 @@
 """The product CLI `dgalerkin mesh.msh config.conf` (dgfem-acoustic_b200/lib/dgalerkin, the reference's command line,
 src/dgalerkin.cpp:11-63) end to end on the GPU: the views it appends to saveFile and the receiver file against the oracle.
 
-Gated (DGB_TEST_CLI=1): written after the round's GPU budget was spent, not yet run on hardware."""
+First run on hardware in round 2 (profiles/r02/cli_tests.log)."""
 import os
 import subprocess
 
@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT, rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DGB_TEST_CLI") != "1", reason="CLI end-to-end test not yet run on hardware: set DGB_TEST_CLI=1")]
+pytestmark = [pytest.mark.gpu]
 
 CONF = """timeStart=0
 timeEnd=0.00205
