@@ -231,7 +231,7 @@ def main():
     ap.add_argument("--cells", type=int, default=62)
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--v0", type=float, nargs=3, default=[0.0, 0.0, 0.0])
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA, 4 / 5 Bernstein-Bezier (sparse operators, CUDA cores; 5 = face-sequential schedule)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA, 4 / 5 Bernstein-Bezier (sparse operators, CUDA cores; 5 = face-sequential schedule), 6 Bernstein-Bezier second generation (TMA pipeline, interleaved layout)")
     ap.add_argument("--bb-tile", type=int, default=0, help="elements per CTA of the Bernstein-Bezier kernels (32, 16, 8; 0: the engine's default)")
     ap.add_argument("--partitioner", default="rcb", choices=["rcb", "metis"], help="element partition for --gpus > 1")
     ap.add_argument("--no-overlap", action="store_true")

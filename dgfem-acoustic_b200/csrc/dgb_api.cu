@@ -135,9 +135,10 @@ struct dgb_handle {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
     std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
     int stageEvUsed = 0;
-    StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, active;
+    StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, bb2Kernel, active;
     // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
-    bool bbMode = false;
+    int bbMode = 0;                  // representation of the resident state: 0 nodal, 1 coefficients [field][el][mesh node order] (stage_bb.cu),
+                                     // 2 coefficients [el][canonical index][field] (stage_bb2.cu)
     int bbTile = 32;                 // elements per CTA of the Bernstein kernels (32, 16, 8)
     std::string bbWhyNot;            // why the Bernstein path is unavailable for this mesh (empty: available)
     // curved (non-affine) meshes: the reference's own tables on the device + inverse element mass matrices; every
@@ -148,13 +149,21 @@ struct dgb_handle {
     CurvedMesh CM{};
     std::vector<void*> curvedAllocs;
     double *dV = nullptr, *dVinv = nullptr;
+    double *dVC = nullptr, *dVinvC = nullptr;  // the same with the coefficient index in canonical order: VC[n][i], VinvC[i][n]
+    uint8_t* dBBTab = nullptr;                 // DeviceMesh::bbTab, followed by the mesh node -> canonical index permutation
+    size_t bbPermOffset = 0;
+    std::vector<uint8_t> permG2C;
+    double *dProbeWBB2 = nullptr, *dRecvWBB2 = nullptr;
     std::vector<double> hostV;       // [Np][Np], u_n = sum_m V[n][m] c_m (mesh node order)
     // Bernstein twins of the probes / receivers (a nodal value is a weighted sum of the element's coefficients) and sources
     int32_t* dProbeElBB = nullptr;
     double *dProbeWBB = nullptr, *dRecvWBB = nullptr;
     std::vector<int32_t> srcElOff;   // per source: its range in dSrcElList
     int32_t *dSrcElList = nullptr, *dSrcNodeOff = nullptr, *dSrcNodeLocal = nullptr;
-    StageKernel autoKernel() const { return ws.launch ? ws : tiled.launch ? tiled : generic; }
+    // Measured on B200 (profiles/r02/): the second-generation Bernstein kernel beats the dense DMMA kernels on tetrahedra of
+    // order >= 3, with and without mean flow
+    StageKernel autoKernel() const { return (bb2Kernel.launch && M.order >= 3 && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
+    bool preferBB2 = false;
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
     bool recvPending = false;  // overlap 2: the halo exchange of the previous stage has not been waited for yet
@@ -244,7 +253,7 @@ void freeHandle(dgb_handle* h) {
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
     for (void* p : h->curvedAllocs) F(p);
-    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
+    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv); F(h->dVC); F(h->dVinvC); F(h->dBBTab); F(h->dProbeWBB2); F(h->dRecvWBB2); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -549,9 +558,39 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                 h->dV = devUpload(S.V);
                 h->dVinv = devUpload(S.Vinv);
                 h->bbSeqKernel = selectBBKernel(dim, d->order, 1);
+                // second generation: canonical coefficient order, interleaved fields
+                h->bb2Kernel = selectBB2Kernel(dim, d->order);
+                {
+                    const int N = d->order;
+                    h->permG2C.assign(Np, 0);
+                    for (int i = 0; i < Np; ++i) h->permG2C[S.T.permC2G[i]] = (uint8_t)i;
+                    std::vector<uint8_t> tab((size_t)4 * Nfp + (size_t)M.nMaps * 4 * Nfp + Np, 0);
+                    for (int J = 0; J < 4; ++J)
+                        for (int b1 = 0; b1 <= N; ++b1)
+                            for (int b2 = 0; b2 <= N - b1; ++b2) {
+                                const int b = bb::fidx(N, b1, b2);
+                                tab[(size_t)J * Nfp + b] = (uint8_t)bb::layerIdxRt(N, J, 0, b1, b2);
+                                for (int mp = 0; mp < M.nMaps; ++mp)
+                                    tab[(size_t)4 * Nfp + ((size_t)mp * 4 + J) * Nfp + b] = h->permG2C[maps[(size_t)mp * Nfp + S.T.facePos[J][b]]];
+                            }
+                    h->bbPermOffset = (size_t)4 * Nfp + (size_t)M.nMaps * 4 * Nfp;
+                    std::copy(h->permG2C.begin(), h->permG2C.end(), tab.begin() + h->bbPermOffset);
+                    h->dBBTab = devUpload(tab);
+                    M.bbTab = h->dBBTab;
+                    for (int J = 0; J < 4; ++J) M.bbFaceLf[J] = S.T.faceLf[J];
+                    std::vector<double> VC((size_t)Np * Np), VinvC((size_t)Np * Np);
+                    for (int n = 0; n < Np; ++n)
+                        for (int i = 0; i < Np; ++i) {
+                            VC[(size_t)n * Np + i] = S.V[(size_t)n * Np + S.T.permC2G[i]];
+                            VinvC[(size_t)i * Np + n] = S.Vinv[(size_t)S.T.permC2G[i] * Np + n];
+                        }
+                    h->dVC = devUpload(VC);
+                    h->dVinvC = devUpload(VinvC);
+                }
             } catch (const std::exception& e) {
                 h->bbWhyNot = e.what();
                 h->bbKernel = StageKernel{};
+                h->bb2Kernel = StageKernel{};
             }
         }
 
@@ -598,6 +637,11 @@ void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     h->launches += nLaunched;
 }
 
+void packHalo(dgb_handle* h, const double* produced, int nSendEl) {
+    if (h->bbMode == 2) launchPackElementsBB2(produced, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+    else launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+}
+
 // Halo exchange of array y (owned border elements -> the peers' halo slots), SURVEY §8 e1.
 void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
     const PartitionPlan& P = h->plan;
@@ -607,6 +651,12 @@ void exchangeHalo(dgb_handle* h, double* y, cudaStream_t s) {
     for (size_t i = 0; i < P.peers.size(); ++i) {
         const int peer = P.peers[i];
         const int nSend = P.sendOffset[i + 1] - P.sendOffset[i], nRecv = P.recvOffset[i + 1] - P.recvOffset[i];
+        if (h->bbMode == 2) {  // interleaved coefficients: an element is one run of 4*Np doubles, one message per peer and direction
+            const int64_t run = 4ll * Np;
+            if (nSend > 0) NCCL_CHECK(nccl().Send(h->sendBuf + (int64_t)P.sendOffset[i] * run, (size_t)nSend * run, ncclDouble, peer, h->comm, s));
+            if (nRecv > 0) NCCL_CHECK(nccl().Recv(y + (int64_t)(P.Kown + P.recvOffset[i]) * run, (size_t)nRecv * run, ncclDouble, peer, h->comm, s));
+            continue;
+        }
         const int64_t totalSend = (int64_t)P.sendElems.size() * Np;
         for (int q = 0; q < 4; ++q) {
             if (nSend > 0)
@@ -743,7 +793,7 @@ void pushHalo(dgb_handle* h, double* produced) {
         F.flag[i] = reinterpret_cast<unsigned long long*>(pm.base + pm.flagOffset) + P.rank;
     }
     ++h->epoch;
-    launchPushHalo(produced, h->M.stride, h->Np, h->dSendElems, h->dSendPeer, h->dSendSlot, (int)P.sendElems.size(), T, h->stream);
+    launchPushHalo(produced, h->M.stride, h->Np, h->dSendElems, h->dSendPeer, h->dSendSlot, (int)P.sendElems.size(), T, h->stream, h->bbMode == 2);
     launchSignalPeers(F, h->epoch, h->stream);
     h->launches += 2;
 }
@@ -802,7 +852,7 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
             h->recvPending = false;
         }
         launchStage(h, A, P.Kinterior, P.Kown, false);
-        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        packHalo(h, produced, nSendEl);
         ++h->launches;
         CUDA_CHECK(cudaEventRecord(h->evBorder, h->stream));
         CUDA_CHECK(cudaStreamWaitEvent(h->commStream, h->evBorder, 0));
@@ -811,7 +861,7 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
         h->recvPending = true;
     } else if (overlap == 1) {
         launchStage(h, A, P.Kinterior, P.Kown, false);
-        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        packHalo(h, produced, nSendEl);
         ++h->launches;
         CUDA_CHECK(cudaEventRecord(h->evBorder, h->stream));
         CUDA_CHECK(cudaStreamWaitEvent(h->commStream, h->evBorder, 0));
@@ -821,7 +871,7 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
         CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
     } else {
         launchStage(h, A, 0, h->M.Kown, true);
-        launchPackElements(produced, h->M.stride, h->Np, h->dSendElems, nSendEl, h->sendBuf, h->stream);
+        packHalo(h, produced, nSendEl);
         ++h->launches;
         exchangeHalo(h, produced, h->stream);
     }
@@ -833,6 +883,40 @@ void finishExchange(dgb_handle* h) {
         CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
         h->recvPending = false;
     }
+}
+
+// Representation of the resident state a stage kernel works on (dgb_handle::bbMode)
+int representationOf(const dgb_handle* h, const StageKernel& k) {
+    if (!k.launch) return 0;
+    if (k.launch == h->bb2Kernel.launch) return 2;
+    if (k.launch == h->bbKernel.launch || k.launch == h->bbSeqKernel.launch) return 1;
+    return 0;
+}
+
+// Converts what is resident (U, owned + halo elements) when the active kernel changes the representation. ACC is the
+// scratch array of the layout-changing conversions (it is dead between steps: the first RK stage overwrites it).
+void setRepresentation(dgb_handle* h, int want) {
+    if (want == h->bbMode) return;
+    finishExchange(h);
+    if (h->stateSet) {
+        const int64_t S = h->M.stride;
+        const int Np = h->Np, K = h->M.Ktot;
+        const size_t bytes = (size_t)4 * S * sizeof(double);
+        if (h->bbMode == 1) { launchElementMatrix(h->U, h->U, S, Np, K, h->dV, h->stream); ++h->launches; }
+        else if (h->bbMode == 2) {
+            launchConvertBB2(h->U, h->ACC, S, Np, K, h->dVC, false, h->stream);
+            CUDA_CHECK(cudaMemcpyAsync(h->U, h->ACC, bytes, cudaMemcpyDeviceToDevice, h->stream));
+            ++h->launches;
+        }
+        if (want == 1) { launchElementMatrix(h->U, h->U, S, Np, K, h->dVinv, h->stream); ++h->launches; }
+        else if (want == 2) {
+            launchConvertBB2(h->U, h->ACC, S, Np, K, h->dVinvC, true, h->stream);
+            CUDA_CHECK(cudaMemcpyAsync(h->U, h->ACC, bytes, cudaMemcpyDeviceToDevice, h->stream));
+            ++h->launches;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    h->bbMode = want;
 }
 
 void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) {
@@ -902,13 +986,15 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
     }
     for (int step = step0; step < nsteps; ++step, t += dt) {
         if (h->nprobe > 0) {
-            if (h->bbMode) launchGatherReceivers(h->U, h->M.stride, h->Np, h->dProbeElBB, h->dProbeWBB, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
+            if (h->bbMode) launchGatherReceivers(h->U, h->M.stride, h->Np, h->dProbeElBB, h->bbMode == 2 ? h->dProbeWBB2 : h->dProbeWBB, h->nprobe,
+                                                 h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream, h->bbMode == 2);
             else launchGatherProbes(h->U, h->M.stride, h->dProbeIdx, h->nprobe, h->dProbeRec + (size_t)h->probeCount * h->nprobe * 4, h->stream);
             ++h->probeCount;
             ++h->launches;
         }
         if (h->nrecv > 0) {  // owned elements only: no halo value is read
-            launchGatherReceivers(h->U, h->M.stride, h->Np, h->dRecvEl, h->bbMode ? h->dRecvWBB : h->dRecvW, h->nrecv, h->dRecvRec + (size_t)h->recvCount * h->nrecv * 4, h->stream);
+            launchGatherReceivers(h->U, h->M.stride, h->Np, h->dRecvEl, h->bbMode == 2 ? h->dRecvWBB2 : h->bbMode ? h->dRecvWBB : h->dRecvW, h->nrecv,
+                                  h->dRecvRec + (size_t)h->recvCount * h->nrecv * 4, h->stream, h->bbMode == 2);
             ++h->recvCount;
             ++h->launches;
         }
@@ -918,7 +1004,8 @@ void runImpl(dgb_handle* h, int integrator, double t, int nsteps, double* tEnd) 
                 const double val = h->srcAmp[s] * sin(2 * M_PI * h->srcFreq[s] * t + h->srcPhase[s]);
                 const int n = h->srcOff[s + 1] - h->srcOff[s];
                 if (h->bbMode) launchSetNodesBB(h->U, h->Np, h->dSrcElList + h->srcElOff[s], h->dSrcNodeOff + h->srcElOff[s], h->dSrcNodeLocal,
-                                                h->srcElOff[s + 1] - h->srcElOff[s] - 1 /* minus the closing entry */, val, h->dV, h->dVinv, h->stream);
+                                                h->srcElOff[s + 1] - h->srcElOff[s] - 1 /* minus the closing entry */, val, h->dV, h->dVinv, h->stream,
+                                                h->bbMode == 2 ? 4 : 1, h->bbMode == 2 ? h->dBBTab + h->bbPermOffset : nullptr);
                 else launchSetNodes(h->U, h->dSrcIdx + h->srcOff[s], n, val, h->stream);
                 if (n > 0) ++h->launches;
             }
@@ -995,6 +1082,13 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
     const int Np = h->Np;
     const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
     if (!h->partitioned) {
+        if (h->bbMode == 2) {  // nodal values land in ACC (dead between steps), the conversion writes the interleaved coefficients
+            CUDA_CHECK(cudaMemcpyAsync(h->ACC, u, (size_t)4 * Ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launchConvertBB2(h->ACC, dst, S, Np, h->M.Ktot, h->dVinvC, true, h->stream);
+            ++h->launches;
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            return;
+        }
         CUDA_CHECK(cudaMemcpyAsync(dst, u, (size_t)4 * Ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, h->M.Ktot, h->dVinv, h->stream); ++h->launches; }  // nodal -> Bernstein
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -1009,9 +1103,10 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
 #pragma omp parallel for schedule(static) num_threads(nth)
         for (int l = 0; l < Ktot; ++l)
             std::memcpy(stage + (size_t)q * S + (size_t)l * Np, u + q * Ng + (int64_t)l2g[l] * Np, Np * sizeof(double));
-        CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)q * S, stage + (size_t)q * S, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync((h->bbMode == 2 ? h->ACC : dst) + (size_t)q * S, stage + (size_t)q * S, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, Ktot, h->dVinv, h->stream); ++h->launches; }  // owned + halo elements
+    if (h->bbMode == 2) { launchConvertBB2(h->ACC, dst, S, Np, Ktot, h->dVinvC, true, h->stream); ++h->launches; }
+    else if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, Ktot, h->dVinv, h->stream); ++h->launches; }  // owned + halo elements
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
@@ -1019,7 +1114,8 @@ void stateToHost(dgb_handle* h, const double* src, double* u) {
     const int Np = h->Np;
     const int64_t Ng = (int64_t)h->Kglobal * Np, S = h->M.stride;
     if (h->bbMode) {  // Bernstein -> nodal into ACC (dead between stages: MODE_RK1 overwrites it), then copy from there
-        launchElementMatrix(src, h->ACC, S, Np, h->M.Kown, h->dV, h->stream);
+        if (h->bbMode == 2) launchConvertBB2(src, h->ACC, S, Np, h->M.Kown, h->dVC, false, h->stream);
+        else launchElementMatrix(src, h->ACC, S, Np, h->M.Kown, h->dV, h->stream);
         ++h->launches;
         src = h->ACC;
     }
@@ -1120,7 +1216,8 @@ int dgb_snapshot_begin(dgb_handle* h, double* u_host) {
             CUDA_CHECK(cudaEventCreateWithFlags(&h->evSnapDone, cudaEventDisableTiming));
         }
         if (h->snapPending) CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evSnapDone, 0));  // the previous copy still reads the buffer
-        if (h->bbMode) { launchElementMatrix(h->U, h->dSnap, h->M.stride, h->Np, h->M.Kown, h->dV, h->stream); ++h->launches; }  // Bernstein -> nodal
+        if (h->bbMode == 2) { launchConvertBB2(h->U, h->dSnap, h->M.stride, h->Np, h->M.Kown, h->dVC, false, h->stream); ++h->launches; }
+        else if (h->bbMode) { launchElementMatrix(h->U, h->dSnap, h->M.stride, h->Np, h->M.Kown, h->dV, h->stream); ++h->launches; }  // Bernstein -> nodal
         else CUDA_CHECK(cudaMemcpyAsync(h->dSnap, h->U, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CUDA_CHECK(cudaEventRecord(h->evSnapReady, h->stream));
         CUDA_CHECK(cudaStreamWaitEvent(h->snapStream, h->evSnapReady, 0));
@@ -1214,6 +1311,13 @@ int dgb_set_probes(dgb_handle* h, int nprobe, const int32_t* nodeIdx) {
             }
             h->dProbeElBB = devUpload(elBB);
             h->dProbeWBB = devUpload(wBB);
+            if (h->dProbeWBB2) { cudaFree(h->dProbeWBB2); h->dProbeWBB2 = nullptr; }
+            if (!h->permG2C.empty()) {
+                std::vector<double> w2(wBB.size());
+                for (int j = 0; j < nprobe; ++j)
+                    for (int m = 0; m < h->Np; ++m) w2[(size_t)j * h->Np + h->permG2C[m]] = wBB[(size_t)j * h->Np + m];
+                h->dProbeWBB2 = devUpload(w2);
+            }
         }
         h->nprobe = nprobe;
         h->probeCap = h->probeCount = 0;
@@ -1263,6 +1367,13 @@ int dgb_set_receivers(dgb_handle* h, int nrecv, const int32_t* el, const double*
                 for (int n = 0; n < h->Np; ++n)
                     for (int m = 0; m < h->Np; ++m) wBB[(size_t)j * h->Np + m] += w[(size_t)j * h->Np + n] * h->hostV[(size_t)n * h->Np + m];
             h->dRecvWBB = devUpload(wBB);
+            if (h->dRecvWBB2) { cudaFree(h->dRecvWBB2); h->dRecvWBB2 = nullptr; }
+            if (!h->permG2C.empty()) {
+                std::vector<double> w2(wBB.size());
+                for (int j = 0; j < nrecv; ++j)
+                    for (int m = 0; m < h->Np; ++m) w2[(size_t)j * h->Np + h->permG2C[m]] = wBB[(size_t)j * h->Np + m];
+                h->dRecvWBB2 = devUpload(w2);
+            }
         }
         h->nrecv = nrecv;
         h->recvCap = h->recvCount = 0;
@@ -1349,19 +1460,13 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             } else if (value == 4 || value == 5) {  // 5: the face-sequential schedule of the same arithmetic
                 if (!h->bbKernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
                 h->active = value == 4 ? h->bbKernel : h->bbSeqKernel;
+            } else if (value == 6) {
+                if (!h->bb2Kernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
+                h->active = h->bb2Kernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes
             if (h->curved) h->curvedName = h->firstCurved > 0 ? std::string(h->active.name) + " + stage_curved" : std::string("stage_curved");
-            const bool wantBB = h->active.launch && (h->active.launch == h->bbKernel.launch || h->active.launch == h->bbSeqKernel.launch);
-            if (wantBB != h->bbMode) {
-                finishExchange(h);
-                if (h->stateSet) {
-                    launchElementMatrix(h->U, h->U, h->M.stride, h->Np, h->M.Ktot, wantBB ? h->dVinv : h->dV, h->stream);
-                    ++h->launches;
-                    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-                }
-                h->bbMode = wantBB;
-            }
+            setRepresentation(h, representationOf(h, h->active));
         } else if (k == "overlap") {
             if (value < -1 || value > 2) throw DgbException(DGB_ERR_ARG, "overlap must be -1 (automatic), 0, 1 or 2");
             h->overlap = value;

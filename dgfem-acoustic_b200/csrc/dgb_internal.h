@@ -45,6 +45,11 @@ struct DeviceMesh {
     int32_t* fflags;  // [Kown][Nf]       bc type | tau sign | map id
     // physics
     double c0, rho0, v0[3];
+    // second-generation Bernstein kernel (stage_bb2.cu): byte tables in canonical order — [4][Nfp] coefficient of face J's
+    // 2D index b, then [nMaps][4][Nfp] the neighbour's coefficient for (face-pairing map, face J, b) — and the mesh's
+    // local face of canonical face J
+    const uint8_t* bbTab;
+    uint8_t bbFaceLf[4];
 };
 
 struct StageArgs {
@@ -72,8 +77,14 @@ StageKernel selectBBKernel(int dim, int order, int variant = 0, int tile = 32); 
 // element's node numbering convention, so one copy per order serves every handle of the process)
 void setBBTables(int order, const bb::Tables& T);
 // hard source in Bernstein mode: elements elList[0..nEl) get the nodal value `value` at their local nodes nodeLocal[nodeOff[b]..nodeOff[b+1])
+// coefStride / perm describe where coefficient m (mesh node order, the order of V / Vinv) of an element lives:
+// field[(el*Np + (perm ? perm[m] : m)) * coefStride]
 void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal, int nEl, double value,
-                      const double* V, const double* Vinv, cudaStream_t s);
+                      const double* V, const double* Vinv, cudaStream_t s, int coefStride = 1, const uint8_t* perm = nullptr);
+// second-generation Bernstein kernel (stage_bb2.cu): interleaved canonical coefficient layout c[(el*Np + i)*4 + q]
+StageKernel selectBB2Kernel(int dim, int order);
+void launchConvertBB2(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, bool toBB, cudaStream_t s);
+void launchPackElementsBB2(const double* y, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 // y = Mat x per element and field over a whole state array (nodal <-> Bernstein conversion); in and out may alias
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s);
 
@@ -81,7 +92,9 @@ struct CurvedMesh;  // curved_setup.h
 void launchCurved(const CurvedMesh& C, const StageArgs& A, cudaStream_t s);  // stage_curved.cu: every element through the reference's own loops
 void launchSetNodes(double* field, const int32_t* idx, int n, double value, cudaStream_t s);
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s);
-void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s);
+// interleaved != 0: u is an interleaved coefficient array c[(el*Np + m)*4 + q] (stage_bb2.cu) and w is in its coefficient order
+void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s,
+                           int interleaved = 0);
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
 
@@ -91,7 +104,7 @@ struct PeerTargets { double* arr[MAX_PEERS]; long long stride[MAX_PEERS]; };   /
 struct PeerFlags { unsigned long long* flag[MAX_PEERS]; int n; };              // THIS rank's slot in each peer's flag array
 struct PeerWait { int rank[MAX_PEERS]; int n; };                               // ranks whose flags this rank waits for
 void launchPushHalo(const double* y, int64_t stride, int Np, const int32_t* sendElems, const int32_t* sendPeer, const int32_t* sendSlot,
-                    int nSend, const PeerTargets& T, cudaStream_t s);
+                    int nSend, const PeerTargets& T, cudaStream_t s, int interleaved = 0);
 void launchSignalPeers(const PeerFlags& F, unsigned long long epoch, cudaStream_t s);
 void launchWaitPeers(const unsigned long long* flags, const PeerWait& W, unsigned long long epoch, unsigned long long timeoutNs, int* err,
                      cudaStream_t s);

@@ -16,8 +16,16 @@ namespace dgb {
 namespace {
 
 __global__ void pushHaloKernel(const double* __restrict__ y, int64_t stride, int Np, const int32_t* __restrict__ sendElems,
-                               const int32_t* __restrict__ sendPeer, const int32_t* __restrict__ sendSlot, int nSend, PeerTargets T) {
+                               const int32_t* __restrict__ sendPeer, const int32_t* __restrict__ sendSlot, int nSend, PeerTargets T, int interleaved) {
     const int64_t per = (int64_t)nSend * Np;
+    if (interleaved) {  // c[(el*Np + i)*4 + q] (stage_bb2.cu): an element is one run of 4*Np doubles
+        const int run = 4 * Np;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * per; i += (int64_t)gridDim.x * blockDim.x) {
+            const int k = (int)(i / run), r = (int)(i - (int64_t)k * run);
+            T.arr[sendPeer[k]][(int64_t)sendSlot[k] * run + r] = y[(int64_t)sendElems[k] * run + r];
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * per; i += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(i / per);
         const int64_t r = i - q * per;
@@ -68,11 +76,11 @@ __global__ void waitPeersKernel(const unsigned long long* flags, PeerWait W, uns
 }  // namespace
 
 void launchPushHalo(const double* y, int64_t stride, int Np, const int32_t* sendElems, const int32_t* sendPeer, const int32_t* sendSlot,
-                    int nSend, const PeerTargets& T, cudaStream_t s) {
+                    int nSend, const PeerTargets& T, cudaStream_t s, int interleaved) {
     const int64_t tot = 4ll * nSend * Np;
     if (tot <= 0) return;
     const unsigned blocks = (unsigned)std::min<int64_t>((tot + 255) / 256, 148 * 8);
-    DGB_LAUNCH(pushHaloKernel, blocks, 256, 0, s, y, stride, Np, sendElems, sendPeer, sendSlot, nSend, T);
+    DGB_LAUNCH(pushHaloKernel, blocks, 256, 0, s, y, stride, Np, sendElems, sendPeer, sendSlot, nSend, T, interleaved);
 }
 
 void launchSignalPeers(const PeerFlags& F, unsigned long long epoch, cudaStream_t s) {

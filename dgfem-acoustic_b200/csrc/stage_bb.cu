@@ -410,12 +410,14 @@ __global__ void __launch_bounds__(256) elementMatrixKernel(const double* in, dou
 // overwrites of different nodes commute),  c += sum_n Vinv[:, n] delta_n  makes (V c)_n = value there and leaves every other
 // nodal value of the element unchanged.
 __global__ void __launch_bounds__(64) setNodesBBKernel(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal,
-                                                       double value, const double* __restrict__ V, const double* __restrict__ Vinv) {
+                                                       double value, const double* __restrict__ V, const double* __restrict__ Vinv, int coefStride,
+                                                       const uint8_t* __restrict__ perm) {
     __shared__ double c[bb::MAX_NP], delta[bb::MAX_NP];
     const int b = blockIdx.x, t = threadIdx.x;
     const int64_t base = (int64_t)elList[b] * Np;
     const int n0 = nodeOff[b], nn = nodeOff[b + 1] - n0;
-    for (int m = t; m < Np; m += blockDim.x) c[m] = field[base + m];
+    auto at = [&](int m) -> double& { return field[(base + (perm ? perm[m] : m)) * coefStride]; };
+    for (int m = t; m < Np; m += blockDim.x) c[m] = at(m);
     __syncthreads();
     for (int k = t; k < nn; k += blockDim.x) {
         const int n = nodeLocal[n0 + k];
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(64) setNodesBBKernel(double* field, int Np, co
     for (int m = t; m < Np; m += blockDim.x) {
         double s = 0.0;
         for (int k = 0; k < nn; ++k) s = fma(Vinv[m * Np + nodeLocal[n0 + k]], delta[k], s);
-        field[base + m] = c[m] + s;
+        at(m) = c[m] + s;
     }
 }
 
@@ -459,8 +461,8 @@ void setBBTables(int order, const bb::Tables& T) {
 }
 
 void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_t* nodeOff, const int32_t* nodeLocal, int nEl, double value,
-                      const double* V, const double* Vinv, cudaStream_t s) {
-    if (nEl > 0) DGB_LAUNCH(setNodesBBKernel, nEl, 64, 0, s, field, Np, elList, nodeOff, nodeLocal, value, V, Vinv);
+                      const double* V, const double* Vinv, cudaStream_t s, int coefStride, const uint8_t* perm) {
+    if (nEl > 0) DGB_LAUNCH(setNodesBBKernel, nEl, 64, 0, s, field, Np, elList, nodeOff, nodeLocal, value, V, Vinv, coefStride, perm);
 }
 
 void launchElementMatrix(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, cudaStream_t s) {

@@ -1,0 +1,450 @@
+// Bernstein-Bezier stage kernel, second generation (dgb_set_option("kernel", 6)): the sparse operators of bb_ops.h behind an
+// asynchronous, warp-private pipeline built on the Blackwell copy engines.
+//
+// Same fused operator as every other stage kernel (updateFlux + numStep + RK axpys of the reference, Mesh.cpp:476-674,
+// solver.cpp:35-52, 261-285) and the same arithmetic as stage_bb.cu (strong form on Bernstein coefficients). What changes is
+// the data layout and who moves the data. The first-generation kernels (stage_bb.cu) were measured on B200 at 2.43 ms per
+// stage on the 1.43 M-tetrahedron order-4 mesh (profiles/r02/): 12 warps per SM, each walking load -> wait -> compute ->
+// gather -> wait -> ... with every memory latency exposed (long-scoreboard stalls 5 per issue) and the L1 data pipe 57 %
+// busy with 8-byte gathers (9.2 sectors per request). Here:
+//
+//   * STATE LAYOUT [element][canonical coefficient][4 fields] (32 B per coefficient). In Bernstein mode the device layout
+//     is free (dgb_set_state / dgb_get_state convert anyway), so the four fields of a coefficient share one 32-byte
+//     sector: a neighbour-trace gather fetches ONE fully used sector instead of four sectors used at 25 %, a tile of 8
+//     consecutive elements is ONE contiguous run of 8*Np*32 bytes in each state array, and the canonical coefficient
+//     order of bb_ops.h removes every permutation look-up from the kernel.
+//   * ONE WARP = ONE PERSISTENT CTA that owns tiles of 8 elements end to end (thread = (element, field), as in
+//     stage_bb_seq). No CTA barrier exists; the warp's own copies are all asynchronous:
+//       - the tile of the stage input, and the RK registers u / acc of the tile, arrive by TMA bulk copies
+//         (cp.async.bulk, mbarrier complete_tx) — no LSU instruction, no register, no L1 wavefront;
+//       - the results leave by TMA bulk stores straight from the shared-memory tiles they were combined in;
+//       - the neighbour traces of ONE face at a time are gathered with 16-byte cp.async (zero-filled on boundary faces),
+//         one neighbour element per instruction (<= 9 cache lines), issued one lift ahead of their use;
+//       - the next tile's stage input is requested as soon as the last face has read the current one, its face metadata
+//         and inverse Jacobian travel in registers one tile ahead.
+//   * 6 warps per SM at order 4 (33 KB of shared memory each): the latency that occupancy hid badly is hidden by the
+//     copies in flight instead.
+//
+// Shared memory of a warp: stage-input tile | acc tile | u tile (3 x 8*Np*32 B) | one face's traces / lift inputs | face
+// coefficients | 2 mbarriers | own-trace index table.
+#include "bb_ops.h"
+#include "dgb_device.cuh"
+#include "dgb_internal.h"
+#include "dgb_launch.h"
+
+namespace dgb {
+
+namespace {
+
+constexpr int kTE2 = 8;  // elements per tile: 8 elements x 4 fields = the 32 lanes of the warp
+
+template <int P>
+struct BB2Cfg {
+    static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
+    static constexpr int TILE = kTE2 * NP * 4;         // doubles of one state tile
+    // element stride of the trace buffer (doubles): NFP*4, padded so that the 128-bit accesses of the face-input phase
+    // (quarter-warp = 2 elements x 4 tasks) and the 64-bit reads of the lift (half-warp = 4 elements x 4 fields) spread
+    // over the banks
+#ifndef DGB_BB2_TRPAD
+#define DGB_BB2_TRPAD 0
+#endif
+    static constexpr int TRS = NFP * 4 + DGB_BB2_TRPAD;
+    static constexpr int ROUNDS = (NFP + 3) / 4;       // face-input tasks of a lane: b = lane%4 + 4r
+    static constexpr int GI = (2 * NFP + 31) / 32;     // gather instructions per (element, face): 2 x 16 B per trace
+    static constexpr int FC = 8;                       // doubles per (element, local face): app, aps, b, c, d, n
+    static constexpr size_t SMEM = (size_t)(3 * TILE + kTE2 * TRS + 32 * FC) * sizeof(double) + 2 * sizeof(unsigned long long) + (size_t)((4 * NFP + 15) / 16 * 16);
+    static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
+};
+
+__device__ __forceinline__ uint32_t sAddr2(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit2(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sAddr2(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sAddr2(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait2(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(sAddr2(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sAddr2(smemDst)),
+                 "l"(__cvta_generic_to_global(gmemSrc)), "r"(bytes), "r"(sAddr2(bar))
+                 : "memory");
+}
+// TMA bulk copy shared -> global (bulk async-group)
+__device__ __forceinline__ void bulkStore(void* gmemDst, const void* smemSrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gmemDst)), "r"(sAddr2(smemSrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous copy that bypasses L1 (a trace sector is used once); srcBytes == 0 writes zeros
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc, uint32_t srcBytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sAddr2(smemDst)), "l"(__cvta_generic_to_global(gmemSrc)), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Volume term of field q of one element whose coefficients lie interleaved ([coefficient][4 fields], canonical order) at
+// col: the same arithmetic as bb::fieldVolume.
+template <int N>
+__device__ __forceinline__ void fieldVolumeInterleaved(int q, const double* col, const double (&gl)[4][3], const double (&v0)[3], bool flow, double rc2,
+                                                       double invRho, double (&out)[bb::tet(N)]) {
+    constexpr int NP = bb::tet(N), ND = bb::tet(N - 1);
+    double t[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) t[i] = 0.0;
+    const int nCoupling = q == 0 ? 3 : 1;
+    const int nPass = nCoupling + (flow ? 1 : 0);
+    for (int pass = 0; pass < nPass; ++pass) {  // run-time trip count: one copy of the body
+        int field;
+        double w[4];
+        if (pass < nCoupling) {
+            field = q == 0 ? 1 + pass : 0;
+            const int x = q == 0 ? pass : q - 1;
+            const double s = q == 0 ? rc2 : invRho;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = s * (x == 0 ? gl[j][0] : x == 1 ? gl[j][1] : gl[j][2]);
+        } else {
+            field = q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = v0[0] * gl[j][0] + v0[1] * gl[j][1] + v0[2] * gl[j][2];
+        }
+        double cc[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) cc[i] = col[i * 4 + field];
+        bb::dirDeriv<N, true>(cc, w, t);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) out[i] = 0.0;
+    bb::elevateAdd<N>(t, -1.0, out);
+}
+
+template <int P>
+__global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
+    using C = BB2Cfg<P>;
+    constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS;
+    extern __shared__ __align__(128) unsigned char smemRaw2[];
+    double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile
+    double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
+    double* const sU = sA + C::TILE;                         // u tile (or the stage input again): loaded, combined in place, stored
+    double* const sT = sU + C::TILE;                         // [8][TRS]  traces of the current face, then its lift inputs
+    double* const sFc = sT + kTE2 * TRS;                     // [32][8]   face coefficients of the tile
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sFc + 32 * C::FC);  // [0] stage input, [1] RK registers
+    unsigned char* const sOwn = reinterpret_cast<unsigned char*>(bars + 2);                    // [4][NFP] coefficient of face J's 2D index b
+
+    const int lane = threadIdx.x, el = lane >> 2, q = lane & 3;
+    const unsigned FULL = 0xffffffffu;
+    const Phys ph = makePhys(M);
+    const bool flow = ph.v0[0] != 0.0 || ph.v0[1] != 0.0 || ph.v0[2] != 0.0;
+    const int mode = A.mode;
+    const bool loadU = mode != MODE_RHS, loadA = mode == MODE_RK2 || mode == MODE_RK3 || mode == MODE_RK4;
+    const bool storeA = mode == MODE_RK1 || mode == MODE_RK2 || mode == MODE_RK3;
+    const double* const uSrc = mode == MODE_EULER ? A.yin : A.u;  // first RK stage: u is the stage input (an L2 hit)
+    double* const uDst = mode == MODE_RK4 ? A.u : A.yout;
+
+    int t = blockIdx.x;
+    if (t >= nTiles) return;
+    if (lane == 0) {
+        mbarInit2(&bars[0], 1);
+        mbarInit2(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = lane; i < 4 * NFP; i += 32) sOwn[i] = M.bbTab[i];
+    __syncwarp();
+
+    // face metadata (lane = (element, local face)) and inverse Jacobian (lane = (element, *)) of tile tt, clamped at the range end
+    auto loadMeta = [&](int tt, int& flags, int& nbr, double (&fg)[4], double (&G)[9]) {
+        const int e = min(A.eBegin + tt * kTE2 + el, A.eEnd - 1);
+        const int ef = e * 4 + q;
+        flags = M.fflags[ef];
+        nbr = M.fnbr[ef];
+        const double2 f0 = *reinterpret_cast<const double2*>(M.fgeo + (int64_t)ef * 4);
+        const double2 f1 = *reinterpret_cast<const double2*>(M.fgeo + (int64_t)ef * 4 + 2);
+        fg[0] = f0.x; fg[1] = f0.y; fg[2] = f1.x; fg[3] = f1.y;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) G[j] = M.Ginv[(int64_t)e * 9 + j];
+    };
+    auto issueY = [&](int tt) {  // lane 0 only
+        const int e0 = A.eBegin + tt * kTE2;
+        const uint32_t bytes = (uint32_t)(min(kTE2, A.eEnd - e0) * NP * 32);
+        mbarExpectTx(&bars[0], bytes);
+        bulkLoad(sY, A.yin + (int64_t)e0 * NP * 4, bytes, &bars[0]);
+    };
+    // traces of canonical face J for the tile whose metadata the lanes hold in (flags, nbr): one neighbour element per
+    // instruction, two 16-byte halves per trace
+    auto issueTraces = [&](int J, int flags, int nbr) {
+        const int lf = M.bbFaceLf[J];
+#pragma unroll
+        for (int r = 0; r < kTE2; ++r) {
+            const int fl = __shfl_sync(FULL, flags, r * 4 + lf);
+            const int nb = __shfl_sync(FULL, nbr, r * 4 + lf);
+            const bool interior = (fl & FLAG_BC_MASK) == FACE_INTERIOR && nb >= 0;
+            const unsigned char* mp = M.bbTab + 4 * NFP + ((fl >> FLAG_MAP_SHIFT) * 4 + J) * NFP;
+#pragma unroll
+            for (int g = 0; g < C::GI; ++g) {
+                const int h = lane + 32 * g, b = h >> 1, half = h & 1;
+                if (b < NFP) {
+                    const double* src = A.yin;
+                    if (interior) src += ((int64_t)nb * NP + mp[b]) * 4 + half * 2;
+                    cpAsync16(sT + r * TRS + b * 4 + half * 2, src, interior ? 16u : 0u);
+                }
+            }
+        }
+        cpCommit();
+    };
+
+    int flags, nbr;
+    double fg[4], G[9];
+    loadMeta(t, flags, nbr, fg, G);
+    if (lane == 0) issueY(t);
+    issueTraces(0, flags, nbr);
+    uint32_t phY = 0, phR = 0;
+
+    for (;;) {
+        const int tn = t + (int)gridDim.x;
+        const bool more = tn < nTiles;
+        const int e0 = A.eBegin + t * kTE2;
+        const uint32_t bytes = (uint32_t)(min(kTE2, A.eEnd - e0) * NP * 32);
+
+        // face coefficients of the tile (lane = (element, local face)), barycentric gradients of the lane's element
+        {
+            const int bc = flags & FLAG_BC_MASK;
+            const double v0n = ph.v0[0] * fg[0] + ph.v0[1] * fg[1] + ph.v0[2] * fg[2];
+            const bb::FaceCoef k = bb::faceCoef(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, fg[3], v0n, ph.c0, ph.rho0);
+            double2* fc = reinterpret_cast<double2*>(sFc + lane * C::FC);
+            fc[0] = make_double2(k.app, k.aps);
+            fc[1] = make_double2(k.b, k.c);
+            fc[2] = make_double2(k.d, fg[0]);
+            fc[3] = make_double2(fg[1], fg[2]);
+        }
+        double gl[4][3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double g0 = G[x * 3 + 0], g1 = G[x * 3 + 1], g2 = G[x * 3 + 2];
+            gl[0][x] = -(g0 + g1 + g2);
+            gl[1][x] = g0;
+            gl[2][x] = g1;
+            gl[3][x] = g2;
+        }
+        // metadata of the next tile: requested now, consumed at the end of this tile
+        int flagsN = 0, nbrN = -1;
+        double fgN[4] = {0, 0, 0, 0}, GN[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (more) loadMeta(tn, flagsN, nbrN, fgN, GN);
+        // RK registers of this tile: needed by the epilogue only
+        if (lane == 0) {
+            bulkWaitRead();  // the stores of the previous tile have read their shared-memory tiles
+            if (loadU) {
+                mbarExpectTx(&bars[1], loadA ? 2 * bytes : bytes);
+                bulkLoad(sU, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+                if (loadA) bulkLoad(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+            }
+        }
+        mbarWait2(&bars[0], phY);
+        phY ^= 1;
+        __syncwarp();
+
+        double out[NP];
+        fieldVolumeInterleaved<P>(q, sY + el * NP * 4, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
+
+#pragma unroll 1
+        for (int J = 0; J < 4; ++J) {
+            const int lf = M.bbFaceLf[J];
+            cpWaitAll();
+            __syncwarp();
+            {   // lift inputs of face J, in place over the traces: lane = (element, task b = q + 4r)
+                const double2* fc = reinterpret_cast<const double2*>(sFc + (el * 4 + lf) * C::FC);
+                const double2 c0 = fc[0], c1 = fc[1], c2 = fc[2], c3 = fc[3];
+                const bb::FaceCoef k = {c0.x, c0.y, c1.x, c1.y, c2.x};
+                const double n[3] = {c2.y, c3.x, c3.y};
+#pragma unroll
+                for (int r = 0; r < C::ROUNDS; ++r) {
+                    const int b = q + 4 * r;
+                    if (b < NFP) {
+                        const double2* o = reinterpret_cast<const double2*>(sY + (el * NP + sOwn[J * NFP + b]) * 4);
+                        double2* tp = reinterpret_cast<double2*>(sT + el * TRS + b * 4);
+                        const double2 o0 = o[0], o1 = o[1], t0 = tp[0], t1 = tp[1];
+                        const double a[4] = {o0.x - t0.x, o0.y - t0.y, o1.x - t1.x, o1.y - t1.y};
+                        double x[4];
+                        bb::faceInput(k, n, a, x);
+                        tp[0] = make_double2(x[0], x[1]);
+                        tp[1] = make_double2(x[2], x[3]);
+                    }
+                }
+            }
+            __syncwarp();
+            double x[NFP];
+#pragma unroll
+            for (int b = 0; b < NFP; ++b) x[b] = sT[el * TRS + b * 4 + q];
+            __syncwarp();  // the trace buffer is free: the next face's traces travel while this face is lifted
+            if (J < 3) issueTraces(J + 1, flags, nbr);
+            else if (more) {
+                issueTraces(0, flagsN, nbrN);
+                if (lane == 0) issueY(tn);  // every read of the stage-input tile is done
+            }
+            double zl[NP];
+            bb::liftFaceLocal<P>(x, zl);
+            switch (J) {  // warp-uniform
+                case 0: bb::scatterAddFace<P, 0>(zl, out); break;
+                case 1: bb::scatterAddFace<P, 1>(zl, out); break;
+                case 2: bb::scatterAddFace<P, 2>(zl, out); break;
+                default: bb::scatterAddFace<P, 3>(zl, out); break;
+            }
+        }
+
+        // fused RK update in the shared-memory tiles of the RK registers, then bulk stores
+        if (loadU) {
+            mbarWait2(&bars[1], phR);
+            phR ^= 1;
+        }
+        {
+            double* const pu = sU + el * NP * 4 + q;
+            double* const pa = sA + el * NP * 4 + q;
+            const double dt = A.dt;
+            switch (mode) {
+                case MODE_RK1:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = k; pu[i * 4] = pu[i * 4] + 0.5 * k; }
+                    break;
+                case MODE_RK2:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = pa[i * 4] + 2 * k; pu[i * 4] = pu[i * 4] + 0.5 * k; }
+                    break;
+                case MODE_RK3:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = pa[i * 4] + 2 * k; pu[i * 4] = pu[i * 4] + k; }
+                    break;
+                case MODE_RK4:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pu[i * 4] = fma(pa[i * 4] + k, 1.0 / 6.0, pu[i * 4]); }
+                    break;
+                case MODE_EULER:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) pu[i * 4] = pu[i * 4] + __dmul_rn(dt, out[i]);
+                    break;
+                default:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) pu[i * 4] = out[i];
+                    break;
+            }
+        }
+        fenceProxyAsync();
+        __syncwarp();
+        if (lane == 0) {
+            bulkStore(uDst + (int64_t)e0 * NP * 4, sU, bytes);
+            if (storeA) bulkStore(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
+            bulkCommit();
+        }
+        if (!more) break;
+        t = tn;
+        flags = flagsN;
+        nbr = nbrN;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fg[j] = fgN[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) G[j] = GN[j];
+    }
+    if (lane == 0) bulkWaitAll();
+}
+
+template <int P>
+void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
+    using C = BB2Cfg<P>;
+    const int nEl = A.eEnd - A.eBegin;
+    if (nEl <= 0) return;
+    static KernelConfig kc;
+    static int perSm[kMaxDevices] = {};
+    const int numSm = configureKernel(kc, stageBB2Kernel<P>, C::SMEM, "stage_bb2");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (perSm[dev] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stageBB2Kernel<P>, 32, C::SMEM) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            throw UnsupportedError("stage_bb2: the kernel does not fit an SM of this device");
+        }
+        perSm[dev] = n;
+    }
+    const int nTiles = (nEl + kTE2 - 1) / kTE2;
+    const int grid = std::max(1, std::min(nTiles, (numSm - std::min(A.smReserve, numSm / 2)) * perSm[dev]));
+    stageBB2Kernel<P><<<grid, 32, C::SMEM, s>>>(M, A, nTiles);
+}
+
+// nodal <-> Bernstein conversion between the field-major nodal layout u[q][el*Np + n] (the reference's, the C ABI's) and the
+// interleaved coefficient layout c[(el*Np + i)*4 + q]. mat is [Np][Np] row-major: toBB: c_i = sum_n mat[i][n] u_n (rows of
+// V^-1 in canonical order); fromBB: u_n = sum_i mat[n][i] c_i (columns of V in canonical order). in != out.
+__global__ void __launch_bounds__(256) convertBB2Kernel(const double* __restrict__ in, double* __restrict__ out, int64_t stride, int Np, int K,
+                                                        const double* __restrict__ mat, int toBB) {
+    extern __shared__ double sx2[];  // [4][E*Np]
+    const int E = 256 / Np;
+    const int e0 = blockIdx.x * E;
+    const int nE = min(E, K - e0);
+    const int tid = threadIdx.x;
+    const int cnt = nE * Np;
+    if (toBB) {
+        if (tid < cnt)
+            for (int q = 0; q < 4; ++q) sx2[q * E * Np + tid] = in[q * stride + (int64_t)e0 * Np + tid];
+    } else {
+        for (int i = tid; i < 4 * cnt; i += 256) sx2[(i & 3) * E * Np + (i >> 2)] = in[(int64_t)e0 * Np * 4 + i];
+    }
+    __syncthreads();
+    if (tid >= cnt) return;
+    const int el = tid / Np, r = tid - el * Np;
+    double acc[4] = {0, 0, 0, 0};
+    for (int m = 0; m < Np; ++m) {
+        const double a = mat[r * Np + m];
+        for (int q = 0; q < 4; ++q) acc[q] = fma(a, sx2[q * E * Np + el * Np + m], acc[q]);
+    }
+    if (toBB) {
+        double2* o = reinterpret_cast<double2*>(out + ((int64_t)e0 * Np + tid) * 4);
+        o[0] = make_double2(acc[0], acc[1]);
+        o[1] = make_double2(acc[2], acc[3]);
+    } else {
+        for (int q = 0; q < 4; ++q) out[q * stride + (int64_t)e0 * Np + tid] = acc[q];
+    }
+}
+
+// whole elements of an interleaved state array: out[k] = y[elems[k]] (pack, elems != nullptr) — 4*Np doubles per element
+__global__ void packElementsBB2Kernel(const double* __restrict__ y, int per, const int32_t* __restrict__ elems, int n, double* __restrict__ buf) {
+    const int64_t tot = (int64_t)n * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / per), r = (int)(i - (int64_t)k * per);
+        buf[i] = y[(int64_t)elems[k] * per + r];
+    }
+}
+
+}  // namespace
+
+StageKernel selectBB2Kernel(int dim, int order) {
+    StageKernel k;
+    if (dim != 3) return k;
+    if (order == 2) { k.launch = &launchBB2<2>; k.name = "stage_bb2<3,2>"; }
+    if (order == 3) { k.launch = &launchBB2<3>; k.name = "stage_bb2<3,3>"; }
+    if (order == 4) { k.launch = &launchBB2<4>; k.name = "stage_bb2<3,4>"; }
+    if (order == 5) { k.launch = &launchBB2<5>; k.name = "stage_bb2<3,5>"; }
+    return k;
+}
+
+void launchConvertBB2(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, bool toBB, cudaStream_t s) {
+    if (K <= 0) return;
+    const int E = 256 / Np;
+    convertBB2Kernel<<<(K + E - 1) / E, 256, (size_t)4 * E * Np * sizeof(double), s>>>(in, out, stride, Np, K, mat, toBB ? 1 : 0);
+}
+
+void launchPackElementsBB2(const double* y, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s) {
+    const int64_t tot = 4ll * n * Np;
+    if (tot <= 0) return;
+    const unsigned blocks = (unsigned)std::min<int64_t>((tot + 255) / 256, 148 * 8);
+    packElementsBB2Kernel<<<blocks, 256, 0, s>>>(y, 4 * Np, elems, n, buf);
+}
+
+}  // namespace dgb

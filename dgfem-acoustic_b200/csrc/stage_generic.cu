@@ -176,16 +176,17 @@ __global__ void gatherProbesKernel(const double* u, int64_t stride, const int32_
     }
 }
 // receiver j, field q: sum_n w[j][n] * u[q][el[j]*Np + n]  (Lagrange interpolation inside one element); el < 0 -> 0
-__global__ void gatherReceiversKernel(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out) {
+__global__ void gatherReceiversKernel(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, int interleaved) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 4 * n) {
         const int j = i >> 2, q = i & 3;
         const int e = el[j];
         double s = 0.0;
         if (e >= 0) {
-            const double* uq = u + q * stride + (int64_t)e * Np;
+            const double* uq = interleaved ? u + (int64_t)e * Np * 4 + q : u + q * stride + (int64_t)e * Np;
+            const int cs = interleaved ? 4 : 1;
             const double* wj = w + (int64_t)j * Np;
-            for (int nd = 0; nd < Np; ++nd) s += wj[nd] * uq[nd];
+            for (int nd = 0; nd < Np; ++nd) s += wj[nd] * uq[nd * cs];
         }
         out[i] = s;
     }
@@ -217,8 +218,8 @@ void launchSetNodes(double* field, const int32_t* idx, int n, double value, cuda
 void launchGatherProbes(const double* u, int64_t stride, const int32_t* idx, int n, double* out, cudaStream_t s) {
     if (n > 0) DGB_LAUNCH(gatherProbesKernel, (4 * n + 255) / 256, 256, 0, s, u, stride, idx, n, out);
 }
-void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s) {
-    if (n > 0) DGB_LAUNCH(gatherReceiversKernel, (4 * n + 127) / 128, 128, 0, s, u, stride, Np, el, w, n, out);
+void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_t* el, const double* w, int n, double* out, cudaStream_t s, int interleaved) {
+    if (n > 0) DGB_LAUNCH(gatherReceiversKernel, (4 * n + 127) / 128, 128, 0, s, u, stride, Np, el, w, n, out, interleaved);
 }
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s) {
     const int64_t tot = 4ll * n * Np;

@@ -36,7 +36,7 @@ CASES = [("cube:3", 2, (0.0, 0.0, 0.0)), ("cube.msh", 3, (30.0, 10.0, 5.0)), ("c
          ("cube:2", 5, (0.0, 0.0, 0.0))]
 
 
-@pytest.mark.parametrize("variant", [4, 5])
+@pytest.mark.parametrize("variant", [4, 5, 6])
 @pytest.mark.parametrize("name,order,v0", CASES)
 def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     mesh = _mesh(pkg, mesh_dir, name, order, v0)
@@ -44,7 +44,7 @@ def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     orc = oracle_mod.Oracle(mesh)
     tile = {2: 8, 3: 16}.get(order, 32)
     eng = pkg.Engine(mesh, options={"bb_tile": tile, "kernel": variant})
-    assert eng.kernel_name == (f"stage_bb<3,{order}>/{tile}" if variant == 4 else f"stage_bb_seq<3,{order}>/{tile}")
+    assert eng.kernel_name == {4: f"stage_bb<3,{order}>/{tile}", 5: f"stage_bb_seq<3,{order}>/{tile}", 6: f"stage_bb2<3,{order}>"}[variant]
     rhs = eng.eval_rhs(u0)
     ref = orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u0)
     for q in range(4):
@@ -63,18 +63,19 @@ def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     eng.close()
 
 
-def test_euler_and_switching_the_representation_with_a_resident_state(pkg, oracle_mod, mesh_dir):
+@pytest.mark.parametrize("first,second", [(4, 3), (6, 3), (4, 6), (6, 5)])
+def test_euler_and_switching_the_representation_with_a_resident_state(pkg, oracle_mod, mesh_dir, first, second):
     mesh = _mesh(pkg, mesh_dir, "cube:3", 4, (0.0, 0.0, 0.0))
     u0 = _state(mesh, 3)
-    eng = pkg.Engine(mesh)
+    eng = pkg.Engine(mesh, options={"kernel": 3})
     eng.set_state(u0)
     eng.run(pkg.EULER1, 0.0, 5)           # warp-specialised kernel, nodal state
-    eng.set_option("kernel", 4)            # converts the resident state to Bernstein coefficients
+    eng.set_option("kernel", first)        # converts the resident state to Bernstein coefficients (layout of that kernel)
     t = 0.0
     for _ in range(5):
         t += mesh.desc.dt
     eng.run(pkg.EULER1, t, 6)
-    eng.set_option("kernel", 0)            # and back
+    eng.set_option("kernel", second)       # and back, or on to the other coefficient layout
     for _ in range(6):
         t += mesh.desc.dt
     eng.run(pkg.EULER1, t, 4)
@@ -86,7 +87,8 @@ def test_euler_and_switching_the_representation_with_a_resident_state(pkg, oracl
     eng.close()
 
 
-def test_sources_probes_receivers_in_bernstein_mode(pkg, oracle_mod, mesh_dir):
+@pytest.mark.parametrize("variant", [4, 6])
+def test_sources_probes_receivers_in_bernstein_mode(pkg, oracle_mod, mesh_dir, variant):
     """Hard source (nodal overwrite expressed on the coefficients), probes and receivers (V-weighted gathers)."""
     model = pkg.Model.make_cube(4, -10.0, 10.0, 3)
     cfg = pkg.Config()
@@ -100,7 +102,7 @@ def test_sources_probes_receivers_in_bernstein_mode(pkg, oracle_mod, mesh_dir):
     el, w = mesh.locate_receivers([(0.3, -0.2, 0.9), (4.0, 4.5, -3.0)])
     steps = 20
     u0 = _state(mesh, 5) * 1e-2
-    eng = pkg.Engine(mesh, options={"kernel": 4})
+    eng = pkg.Engine(mesh, options={"kernel": variant})
     eng.set_sources_from_config()
     eng.set_probes(probes)
     eng.set_receivers(el, w)
