@@ -570,6 +570,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                             for (int b2 = 0; b2 <= N - b1; ++b2) {
                                 const int b = bb::fidx(N, b1, b2);
                                 tab[(size_t)J * Nfp + b] = (uint8_t)bb::layerIdxRt(N, J, 0, b1, b2);
+                                M.bbOwn[J][b] = tab[(size_t)J * Nfp + b];
                                 for (int mp = 0; mp < M.nMaps; ++mp)
                                     tab[(size_t)4 * Nfp + ((size_t)mp * 4 + J) * Nfp + b] = h->permG2C[maps[(size_t)mp * Nfp + S.T.facePos[J][b]]];
                             }

@@ -50,6 +50,7 @@ struct DeviceMesh {
     // local face of canonical face J
     const uint8_t* bbTab;
     uint8_t bbFaceLf[4];
+    uint8_t bbOwn[4][28];  // the first table again, in the kernel's parameter space (uniform run-time index)
 };
 
 struct StageArgs {

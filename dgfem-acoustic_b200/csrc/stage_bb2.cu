@@ -42,17 +42,11 @@ template <int P>
 struct BB2Cfg {
     static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
     static constexpr int TILE = kTE2 * NP * 4;         // doubles of one state tile
-    // element stride of the trace buffer (doubles): NFP*4, padded so that the 128-bit accesses of the face-input phase
-    // (quarter-warp = 2 elements x 4 tasks) and the 64-bit reads of the lift (half-warp = 4 elements x 4 fields) spread
-    // over the banks
-#ifndef DGB_BB2_TRPAD
-#define DGB_BB2_TRPAD 0
-#endif
-    static constexpr int TRS = NFP * 4 + DGB_BB2_TRPAD;
-    static constexpr int ROUNDS = (NFP + 3) / 4;       // face-input tasks of a lane: b = lane%4 + 4r
+    static constexpr int TRS = NFP * 4;                // element stride of the trace buffer: the 64-bit reads of lane (element, field) are conflict free
     static constexpr int GI = (2 * NFP + 31) / 32;     // gather instructions per (element, face): 2 x 16 B per trace
-    static constexpr int FC = 8;                       // doubles per (element, local face): app, aps, b, c, d, n
-    static constexpr size_t SMEM = (size_t)(3 * TILE + kTE2 * TRS + 32 * FC) * sizeof(double) + 2 * sizeof(unsigned long long) + (size_t)((4 * NFP + 15) / 16 * 16);
+    static constexpr int FCS = 10;                     // doubles per (local face, element): app, aps, b, c, d, n (+2: conflict-free 128-bit reads)
+    static constexpr size_t SMEM = (size_t)(2 * TILE + kTE2 * TRS + 32 * FCS + 4 /* dummy gather target */) * sizeof(double) + 4 * sizeof(unsigned long long) +
+                                   2 * 32 * sizeof(int2);
     static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
 };
 
@@ -82,6 +76,9 @@ __device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uin
 __device__ __forceinline__ void bulkStore(void* gmemDst, const void* smemSrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gmemDst)), "r"(sAddr2(smemSrc)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void bulkPrefetchL2(const void* gmemSrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gmemSrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -134,13 +131,13 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     using C = BB2Cfg<P>;
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS;
     extern __shared__ __align__(128) unsigned char smemRaw2[];
-    double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile
+    double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
-    double* const sU = sA + C::TILE;                         // u tile (or the stage input again): loaded, combined in place, stored
-    double* const sT = sU + C::TILE;                         // [8][TRS]  traces of the current face, then its lift inputs
-    double* const sFc = sT + kTE2 * TRS;                     // [32][8]   face coefficients of the tile
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sFc + 32 * C::FC);  // [0] stage input, [1] RK registers
-    unsigned char* const sOwn = reinterpret_cast<unsigned char*>(bars + 2);                    // [4][NFP] coefficient of face J's 2D index b
+    double* const sT = sA + C::TILE;                         // [8][TRS]  traces of the current face
+    double* const sFc = sT + kTE2 * TRS;                     // [4][8][FCS] face coefficients of the tile
+    double* const sDummy = sFc + 32 * C::FCS;                // target of the idle gather lanes
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sDummy + 4);  // [0] stage input, [1] u, [2] acc
+    int2* const sMeta = reinterpret_cast<int2*>(bars + 4);   // [2][32] (flags, neighbour) per (element, local face): this tile / the next one
 
     const int lane = threadIdx.x, el = lane >> 2, q = lane & 3;
     const unsigned FULL = 0xffffffffu;
@@ -157,9 +154,9 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     if (lane == 0) {
         mbarInit2(&bars[0], 1);
         mbarInit2(&bars[1], 1);
+        mbarInit2(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = lane; i < 4 * NFP; i += 32) sOwn[i] = M.bbTab[i];
     __syncwarp();
 
     // face metadata (lane = (element, local face)) and inverse Jacobian (lane = (element, *)) of tile tt, clamped at the range end
@@ -174,30 +171,29 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
 #pragma unroll
         for (int j = 0; j < 9; ++j) G[j] = M.Ginv[(int64_t)e * 9 + j];
     };
+    auto tileBytes = [&](int tt) { return (uint32_t)(min(kTE2, A.eEnd - (A.eBegin + tt * kTE2)) * NP * 32); };
     auto issueY = [&](int tt) {  // lane 0 only
-        const int e0 = A.eBegin + tt * kTE2;
-        const uint32_t bytes = (uint32_t)(min(kTE2, A.eEnd - e0) * NP * 32);
+        const uint32_t bytes = tileBytes(tt);
         mbarExpectTx(&bars[0], bytes);
-        bulkLoad(sY, A.yin + (int64_t)e0 * NP * 4, bytes, &bars[0]);
+        bulkLoad(sY, A.yin + (int64_t)(A.eBegin + tt * kTE2) * NP * 4, bytes, &bars[0]);
     };
-    // traces of canonical face J for the tile whose metadata the lanes hold in (flags, nbr): one neighbour element per
-    // instruction, two 16-byte halves per trace
-    auto issueTraces = [&](int J, int flags, int nbr) {
+    // traces of canonical face J for the tile whose (flags, neighbour) pairs lie in meta: one neighbour element per
+    // instruction (<= 9 cache lines), two 16-byte halves per trace; boundary faces and idle lanes copy zeros
+    auto issueTraces = [&](int J, const int2* meta) {
         const int lf = M.bbFaceLf[J];
+        const unsigned char* tab = M.bbTab + 4 * NFP + J * NFP;
 #pragma unroll
         for (int r = 0; r < kTE2; ++r) {
-            const int fl = __shfl_sync(FULL, flags, r * 4 + lf);
-            const int nb = __shfl_sync(FULL, nbr, r * 4 + lf);
-            const bool interior = (fl & FLAG_BC_MASK) == FACE_INTERIOR && nb >= 0;
-            const unsigned char* mp = M.bbTab + 4 * NFP + ((fl >> FLAG_MAP_SHIFT) * 4 + J) * NFP;
+            const int2 m = meta[r * 4 + lf];
+            const bool interior = (m.x & FLAG_BC_MASK) == FACE_INTERIOR && m.y >= 0;
+            const unsigned char* mp = tab + (m.x >> FLAG_MAP_SHIFT) * (4 * NFP);
+            const double* base = A.yin + (int64_t)(interior ? m.y : 0) * (NP * 4);
 #pragma unroll
             for (int g = 0; g < C::GI; ++g) {
                 const int h = lane + 32 * g, b = h >> 1, half = h & 1;
-                if (b < NFP) {
-                    const double* src = A.yin;
-                    if (interior) src += ((int64_t)nb * NP + mp[b]) * 4 + half * 2;
-                    cpAsync16(sT + r * TRS + b * 4 + half * 2, src, interior ? 16u : 0u);
-                }
+                const bool act = b < NFP;
+                const int ci = (act && interior) ? mp[b] : 0;
+                cpAsync16(act ? sT + r * TRS + b * 4 + half * 2 : sDummy + half * 2, base + ci * 4 + half * 2, (act && interior) ? 16u : 0u);
             }
         }
         cpCommit();
@@ -207,21 +203,26 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     double fg[4], G[9];
     loadMeta(t, flags, nbr, fg, G);
     if (lane == 0) issueY(t);
-    issueTraces(0, flags, nbr);
-    uint32_t phY = 0, phR = 0;
+    sMeta[lane] = make_int2(flags, nbr);
+    __syncwarp();
+    issueTraces(0, sMeta);
+    uint32_t phY = 0, phU = 0, phA = 0;
+    int mb = 0;  // which half of sMeta holds this tile
 
     for (;;) {
         const int tn = t + (int)gridDim.x;
         const bool more = tn < nTiles;
         const int e0 = A.eBegin + t * kTE2;
-        const uint32_t bytes = (uint32_t)(min(kTE2, A.eEnd - e0) * NP * 32);
+        const uint32_t bytes = tileBytes(t);
+        const int2* const meta = sMeta + 32 * mb;
+        int2* const metaN = sMeta + 32 * (mb ^ 1);
 
         // face coefficients of the tile (lane = (element, local face)), barycentric gradients of the lane's element
         {
             const int bc = flags & FLAG_BC_MASK;
             const double v0n = ph.v0[0] * fg[0] + ph.v0[1] * fg[1] + ph.v0[2] * fg[2];
             const bb::FaceCoef k = bb::faceCoef(bc, (flags & FLAG_TAU_NEG) ? -1.0 : 1.0, fg[3], v0n, ph.c0, ph.rho0);
-            double2* fc = reinterpret_cast<double2*>(sFc + lane * C::FC);
+            double2* fc = reinterpret_cast<double2*>(sFc + (q * 8 + el) * C::FCS);
             fc[0] = make_double2(k.app, k.aps);
             fc[1] = make_double2(k.b, k.c);
             fc[2] = make_double2(k.d, fg[0]);
@@ -236,18 +237,16 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
             gl[2][x] = g1;
             gl[3][x] = g2;
         }
-        // metadata of the next tile: requested now, consumed at the end of this tile
+        // metadata of the next tile: requested now, consumed during the last face of this tile
         int flagsN = 0, nbrN = -1;
         double fgN[4] = {0, 0, 0, 0}, GN[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (more) loadMeta(tn, flagsN, nbrN, fgN, GN);
-        // RK registers of this tile: needed by the epilogue only
         if (lane == 0) {
-            bulkWaitRead();  // the stores of the previous tile have read their shared-memory tiles
-            if (loadU) {
-                mbarExpectTx(&bars[1], loadA ? 2 * bytes : bytes);
-                bulkLoad(sU, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
-                if (loadA) bulkLoad(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+            if (loadA) {  // needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
+                mbarExpectTx(&bars[2], bytes);
+                bulkLoad(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
             }
+            if (more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
         }
         mbarWait2(&bars[0], phY);
         phY ^= 1;
@@ -259,37 +258,47 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
 #pragma unroll 1
         for (int J = 0; J < 4; ++J) {
             const int lf = M.bbFaceLf[J];
+            // lift inputs of face J for this lane's (element, field), straight into registers. With a = own - neighbour
+            // (boundary: the neighbour trace is zero), S = n . a_v, the reference's fluxes read (bb_ops.h: faceInput)
+            //   x_p = app a_p + aps S,   x_v = b a_v + n_v (c a_p + d S):
+            // every lane forms a for its own field, the quad exchanges a_p and S by shuffles
+            double A1, A2, A3, nq;
+            {
+                const double2* fc = reinterpret_cast<const double2*>(sFc + (lf * 8 + el) * C::FCS);
+                const double2 c0 = fc[0], c1 = fc[1], c2 = fc[2], c3 = fc[3];
+                const double nv = q == 1 ? c2.y : q == 2 ? c3.x : c3.y;
+                nq = q == 0 ? 0.0 : nv;
+                A1 = q == 0 ? c0.x : c1.x;
+                A2 = q == 0 ? 0.0 : nv * c1.y;
+                A3 = q == 0 ? c0.y : nv * c2.x;
+            }
             cpWaitAll();
             __syncwarp();
-            {   // lift inputs of face J, in place over the traces: lane = (element, task b = q + 4r)
-                const double2* fc = reinterpret_cast<const double2*>(sFc + (el * 4 + lf) * C::FC);
-                const double2 c0 = fc[0], c1 = fc[1], c2 = fc[2], c3 = fc[3];
-                const bb::FaceCoef k = {c0.x, c0.y, c1.x, c1.y, c2.x};
-                const double n[3] = {c2.y, c3.x, c3.y};
-#pragma unroll
-                for (int r = 0; r < C::ROUNDS; ++r) {
-                    const int b = q + 4 * r;
-                    if (b < NFP) {
-                        const double2* o = reinterpret_cast<const double2*>(sY + (el * NP + sOwn[J * NFP + b]) * 4);
-                        double2* tp = reinterpret_cast<double2*>(sT + el * TRS + b * 4);
-                        const double2 o0 = o[0], o1 = o[1], t0 = tp[0], t1 = tp[1];
-                        const double a[4] = {o0.x - t0.x, o0.y - t0.y, o1.x - t1.x, o1.y - t1.y};
-                        double x[4];
-                        bb::faceInput(k, n, a, x);
-                        tp[0] = make_double2(x[0], x[1]);
-                        tp[1] = make_double2(x[2], x[3]);
-                    }
-                }
-            }
-            __syncwarp();
             double x[NFP];
+            const double* const own = sY + el * NP * 4 + q;
+            const double* const tr = sT + el * TRS + q;
 #pragma unroll
-            for (int b = 0; b < NFP; ++b) x[b] = sT[el * TRS + b * 4 + q];
+            for (int b = 0; b < NFP; ++b) {
+                const double a = own[M.bbOwn[J][b] * 4] - tr[b * 4];
+                const double c = nq * a;
+                const double s1 = c + __shfl_xor_sync(FULL, c, 1);
+                const double S = s1 + __shfl_xor_sync(FULL, s1, 2);
+                const double ap = __shfl_sync(FULL, a, 0, 4);
+                x[b] = A1 * a + (A2 * ap + A3 * S);
+            }
             __syncwarp();  // the trace buffer is free: the next face's traces travel while this face is lifted
-            if (J < 3) issueTraces(J + 1, flags, nbr);
-            else if (more) {
-                issueTraces(0, flagsN, nbrN);
-                if (lane == 0) issueY(tn);  // every read of the stage-input tile is done
+            if (J < 3) issueTraces(J + 1, meta);
+            else {
+                // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
+                if (lane == 0 && loadU) {
+                    mbarExpectTx(&bars[1], bytes);
+                    bulkLoad(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+                }
+                if (more) {
+                    metaN[lane] = make_int2(flagsN, nbrN);
+                    __syncwarp();
+                    issueTraces(0, metaN);
+                }
             }
             double zl[NP];
             bb::liftFaceLocal<P>(x, zl);
@@ -302,12 +311,10 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         }
 
         // fused RK update in the shared-memory tiles of the RK registers, then bulk stores
-        if (loadU) {
-            mbarWait2(&bars[1], phR);
-            phR ^= 1;
-        }
+        if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
+        if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
         {
-            double* const pu = sU + el * NP * 4 + q;
+            double* const pu = sY + el * NP * 4 + q;
             double* const pa = sA + el * NP * 4 + q;
             const double dt = A.dt;
             switch (mode) {
@@ -340,12 +347,17 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         fenceProxyAsync();
         __syncwarp();
         if (lane == 0) {
-            bulkStore(uDst + (int64_t)e0 * NP * 4, sU, bytes);
+            bulkStore(uDst + (int64_t)e0 * NP * 4, sY, bytes);
             if (storeA) bulkStore(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
             bulkCommit();
+            if (more) {
+                bulkWaitRead();  // both tiles have been read by the stores
+                issueY(tn);
+            }
         }
         if (!more) break;
         t = tn;
+        mb ^= 1;
         flags = flagsN;
         nbr = nbrN;
 #pragma unroll
