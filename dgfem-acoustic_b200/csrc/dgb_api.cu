@@ -163,7 +163,7 @@ struct dgb_handle {
     // Measured on B200 (profiles/r02/): the second-generation Bernstein kernel beats the dense DMMA kernels on tetrahedra of
     // order >= 3, with and without mean flow
     StageKernel autoKernel() const { return (bb2Kernel.launch && M.order >= 3 && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
-    bool preferBB2 = false;
+    bool preferBB2 = true;
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
     bool recvPending = false;  // overlap 2: the halo exchange of the previous stage has not been waited for yet
@@ -353,6 +353,8 @@ HostOperators buildOperators(const dgb_desc* d) {
     }
     return H;
 }
+
+int representationOf(const dgb_handle* h, const StageKernel& k);
 
 void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, const void* ncclId, dgb_handle** out) {
     if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
@@ -595,6 +597,10 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
             }
         }
 
+        if (!curved) {  // the automatic choice may be a Bernstein kernel: the (still empty) state then lives in its representation
+            h->active = h->autoKernel();
+            h->bbMode = representationOf(h, h->active);
+        }
         if (h->partitioned) {
             CUDA_CHECK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
             CUDA_CHECK(cudaEventCreateWithFlags(&h->evBorder, cudaEventDisableTiming));

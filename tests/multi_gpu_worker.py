@@ -62,7 +62,7 @@ def main():
     dist.barrier()
     eng.close()
     if rank == 0:
-        single = pkg.Engine(mesh)
+        single = pkg.Engine(mesh, options={"kernel": kernel} if kernel else None)
         single.set_sources_from_config()
         single.set_probes(probes)
         single.set_state(u0)

@@ -222,25 +222,27 @@ def test_error_behaviour(pkg, mesh_dir):
         eng.set_option("overlap", 3)
     flow = build_mesh(pkg, mesh_dir, "cube:2", 4, (10.0, 0.0, 0.0))
     eng2 = pkg.Engine(flow)
+    assert "bb2" in eng2.kernel_name  # the automatic choice for tetrahedra of order >= 3, with or without mean flow
+    eng2.set_option("kernel", 2)
     assert "tiled" in eng2.kernel_name  # mean flow: the warp-specialised kernel is not offered
     with pytest.raises(pkg.DgbError):
         eng2.set_option("kernel", 3)
 
 
-KERNEL_IDS = {"generic": 1, "tiled": 2, "ws": 3}
+KERNEL_IDS = {"generic": 1, "tiled": 2, "ws": 3, "bb2": 6}
 
 
 @pytest.mark.parametrize("name,order,v0", [("cube.msh", 3, (30.0, 10.0, 5.0)), ("sphere.msh", 4, (0, 0, 0)), ("cube:5", 4, (30.0, 10.0, 0.0)),
                                            ("cube:3", 3, (0.0, 0.0, 0.0)), ("cube.msh", 4, (0.0, 0.0, 0.0)), ("cube:1", 4, (0.0, 0.0, 0.0))])
 def test_dmma_kernels_vs_generic_and_oracle(pkg, oracle_mod, mesh_dir, name, order, v0):
-    """The FP64 tensor-core kernels (tiled; warp-specialised for zero mean flow) and the CUDA-core kernel are independent
-    implementations of the same operator. cube:1 (6 elements) and the shipped meshes give ragged last tiles."""
+    """The FP64 tensor-core kernels (tiled; warp-specialised for zero mean flow), the Bernstein kernel and the CUDA-core kernel
+    are independent implementations of the same operator. cube:1 (6 elements) and the shipped meshes give ragged last tiles."""
     mesh = build_mesh(pkg, mesh_dir, name, order, v0)
     u = np.random.default_rng(5).standard_normal((4, mesh.N))
     ref = oracle_mod.Oracle(mesh).eval_rhs(oracle_mod.Oracle.OPERATOR, u)
     eng = pkg.Engine(mesh)
-    kernels = ["generic", "tiled"] + (["ws"] if all(v == 0 for v in v0) else [])
-    assert ("ws" if "ws" in kernels else "tiled") in eng.kernel_name  # the automatic choice
+    kernels = ["generic", "tiled"] + (["ws"] if all(v == 0 for v in v0) else []) + ["bb2"]
+    assert "bb2" in eng.kernel_name  # the automatic choice for tetrahedra of order >= 3 (second-generation Bernstein kernel)
     for kern in kernels:
         eng.set_option("kernel", KERNEL_IDS[kern])
         assert kern in eng.kernel_name
@@ -265,7 +267,7 @@ def test_ws_kernel_rk4_vs_oracle_many_tiles(pkg, oracle_mod, mesh_dir):
     """Warp-specialised kernel over many tiles per CTA (ring buffers wrap several times), against the oracle."""
     mesh = build_mesh(pkg, mesh_dir, "cube:9", 4, (0.0, 0.0, 0.0))  # 4374 tets = 547 tiles -> 3-4 tiles per CTA
     u0 = smooth_state(mesh)
-    eng = pkg.Engine(mesh)
+    eng = pkg.Engine(mesh, options={"kernel": 3})
     assert "ws" in eng.kernel_name
     eng.set_state(u0)
     eng.run(pkg.RUNGE_KUTTA, 0.0, 10)
@@ -280,7 +282,7 @@ def test_ws_kernel_deep_rings(pkg, mesh_dir):
     """48 000 tets = 6000 tiles (40 per CTA): the warp-specialised kernel against the CUDA-core kernel."""
     mesh = build_mesh(pkg, mesh_dir, "cube:20", 4, (0.0, 0.0, 0.0))
     u = np.random.default_rng(11).standard_normal((4, mesh.N))
-    eng = pkg.Engine(mesh)
+    eng = pkg.Engine(mesh, options={"kernel": 3})
     assert "ws" in eng.kernel_name
     a = eng.eval_rhs(u)
     eng.set_option("kernel", 1)
@@ -289,13 +291,15 @@ def test_ws_kernel_deep_rings(pkg, mesh_dir):
         assert rel_l2(a[q], b[q]) < 1e-12
 
 
-def test_ws_kernel_is_deterministic(pkg, mesh_dir):
-    """The warp-specialised kernel hands tiles between warp roles through shared-memory rings and mbarriers; a missed
-    ordering would show up as run-to-run differences. Same input, same launch configuration -> bit-identical results."""
+@pytest.mark.parametrize("kernel,tag", [(3, "ws"), (6, "bb2")])
+def test_ws_kernel_is_deterministic(pkg, mesh_dir, kernel, tag):
+    """The warp-specialised kernel hands tiles between warp roles through shared-memory rings and mbarriers, the Bernstein
+    kernel between the copy engines and its warp through mbarriers and async-proxy fences; a missed ordering would show up
+    as run-to-run differences. Same input, same launch configuration -> bit-identical results."""
     mesh = build_mesh(pkg, mesh_dir, "cube:12", 4, (0.0, 0.0, 0.0))  # 10 368 tets = 1 296 tiles, ~9 per CTA
     u0 = np.random.default_rng(17).standard_normal((4, mesh.N))
-    eng = pkg.Engine(mesh)
-    assert "ws" in eng.kernel_name
+    eng = pkg.Engine(mesh, options={"kernel": kernel})
+    assert tag in eng.kernel_name
     runs = []
     for _ in range(3):
         eng.set_state(u0)
@@ -320,6 +324,7 @@ def test_cuda_graph_of_a_step_equals_eager_launches(pkg, mesh_dir, name, order):
         tend[mode] = eng.run(pkg.RUNGE_KUTTA, tend[mode], 25)  # second call re-uses the instantiated graph
         out[mode] = eng.get_state().copy()
         launches[mode] = eng.launch_count
+        conversions = 2 if "bb" in eng.kernel_name else 0  # Bernstein kernels: dgb_set_state / dgb_get_state each launch one conversion
         eng.close()
     assert np.array_equal(out[0], out[1])
-    assert tend[0] == tend[1] and launches[0] == launches[1] == 4 * 65
+    assert tend[0] == tend[1] and launches[0] == launches[1] == 4 * 65 + conversions

@@ -1,5 +1,7 @@
 """Domain decomposition across GPUs: partitioned run == single-GPU run, for every halo-exchange overlap
-mode (0 none, 1 same stage, 2 next stage, -1 automatic), with and without mean flow (both DMMA kernels). Needs >= 2 CUDA devices; one process per GPU, NCCL halo exchange."""
+mode (0 none, 1 same stage, 2 next stage, -1 automatic), with and without mean flow, for every stage kernel. Needs >= 2 CUDA
+devices; one process per GPU, NCCL halo exchange or direct peer-to-peer stores. (Driver-side evidence on a 1-GPU box: the
+`parity` object of every multi-GPU bench.py line, and profiles/r02/multi_gpu_tests.log.)"""
 import os
 import subprocess
 import sys
@@ -21,37 +23,31 @@ def _device_count():
         return 0
 
 
-@pytest.mark.parametrize("world,cells,order,overlap,flow", [(2, 6, 4, 1, 1), (2, 6, 4, 0, 1), (2, 5, 2, 1, 1), (2, 6, 4, 1, 0), (2, 7, 4, 0, 0), (2, 6, 4, 2, 0), (2, 6, 4, 2, 1),
-                                                                (2, 5, 2, 2, 1), (2, 6, 4, -1, 0)])
-def test_partitioned_equals_single(tmp_path, world, cells, order, overlap, flow):
-    _run_and_compare(tmp_path, world, cells, order, overlap, flow, 0)
+# kernel 0 = the automatic choice (the second-generation Bernstein kernel for tetrahedra of order >= 3: the halo carries
+# interleaved coefficients; the CUDA-core kernel at order 2), 2 / 3 = the DMMA kernels, 4 = the first-generation Bernstein kernel
+@pytest.mark.parametrize("world,cells,order,overlap,flow,kernel", [
+    (2, 6, 4, 1, 1, 0), (2, 6, 4, 0, 1, 0), (2, 5, 2, 1, 1, 0), (2, 6, 4, 1, 0, 0), (2, 7, 4, 0, 0, 0), (2, 6, 4, 2, 0, 0), (2, 6, 4, 2, 1, 0),
+    (2, 5, 2, 2, 1, 0), (2, 6, 4, -1, 0, 0), (2, 6, 3, 0, 1, 0),
+    (2, 6, 4, 1, 1, 2), (2, 6, 4, 0, 0, 3), (2, 6, 4, 1, 0, 3), (2, 6, 4, 2, 0, 3), (2, 6, 4, 2, 1, 2), (2, 6, 4, 0, 0, 4), (2, 6, 3, 1, 1, 4)])
+def test_partitioned_equals_single(tmp_path, world, cells, order, overlap, flow, kernel):
+    _run_and_compare(tmp_path, world, cells, order, overlap, flow, 0, kernel)
 
 
-_UNVERIFIED = pytest.mark.skipif(os.environ.get("DGB_TEST_P2P") != "1", reason="not yet run on hardware (the round's GPU budget was spent): set DGB_TEST_P2P=1")
-
-
-@pytest.mark.parametrize("world,cells,order,overlap,flow", [
-    (2, 6, 4, 0, 0),  # verified on 2 B200s
-    pytest.param(2, 6, 4, 1, 1, marks=_UNVERIFIED), pytest.param(2, 5, 2, 1, 1, marks=_UNVERIFIED), pytest.param(2, 7, 4, 0, 1, marks=_UNVERIFIED)])
-def test_partitioned_equals_single_direct_exchange(tmp_path, world, cells, order, overlap, flow):
+@pytest.mark.parametrize("world,cells,order,overlap,flow,kernel", [
+    (2, 6, 4, 0, 0, 0), (2, 6, 4, 1, 1, 0), (2, 5, 2, 1, 1, 0), (2, 7, 4, 0, 1, 0), (2, 6, 4, 0, 0, 3), (2, 6, 4, 1, 1, 2), (2, 6, 4, 0, 1, 4)])
+def test_partitioned_equals_single_direct_exchange(tmp_path, world, cells, order, overlap, flow, kernel):
     """dgb_set_option("exchange", 1): stores into the peers' halo slots over NVLink + epoch flags (csrc/halo_p2p.cu)."""
-    _run_and_compare(tmp_path, world, cells, order, overlap, flow, 1)
-
-
-@pytest.mark.skipif(os.environ.get("DGB_TEST_BB") != "1", reason="Bernstein-Bezier kernel not yet run on hardware: set DGB_TEST_BB=1")
-@pytest.mark.parametrize("world,cells,order,overlap,flow,exchange", [(2, 6, 4, 0, 0, 0), (2, 6, 3, 1, 1, 0), (2, 6, 4, 0, 1, 1)])
-def test_partitioned_equals_single_bernstein(tmp_path, world, cells, order, overlap, flow, exchange):
-    """Partitioned run with the Bernstein-Bezier kernel (the halo carries coefficients) == single-GPU run with the default kernels."""
-    _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, kernel=4, tol=1e-10)
+    _run_and_compare(tmp_path, world, cells, order, overlap, flow, 1, kernel)
 
 
 def _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, kernel=0, tol=1e-12):
+    """The single-GPU run on rank 0 uses the same kernel as the partitioned run: the two must agree to rounding."""
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     worker = Path(__file__).resolve().parent / "multi_gpu_worker.py"
     steps = 12
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29000 + overlap * 7 + order + 20 * flow + cells + 100 * exchange + 200 * (kernel > 0)), str(worker), str(tmp_path),
+           "--master-port", str(29000 + overlap * 7 + order + 20 * flow + cells + 100 * exchange + 200 * kernel), str(worker), str(tmp_path),
            str(cells), str(order), str(steps), str(overlap), str(flow), str(exchange), str(kernel)]
     subprocess.run(cmd, check=True, timeout=600)
     single = np.load(tmp_path / "single.npz")
