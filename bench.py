@@ -144,12 +144,13 @@ def build_workload(pkg, cells, order, v0):
 def measured_traffic(kernel_name, K):
     """DRAM bytes per launch of the stage kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json:
     dram__bytes_read.sum + dram__bytes_write.sum of one launch, per element of the profiled mesh), scaled to K elements."""
-    p = ROOT / "profiles" / "r01_traffic.json"
-    try:
-        rec = json.loads(p.read_text())[kernel_name]
-        return rec["dram_bytes_per_element"] * K, rec
-    except Exception:
-        return None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):  # newest capture that knows this kernel
+        try:
+            rec = json.loads((ROOT / "profiles" / name).read_text())[kernel_name]
+            return rec["dram_bytes_per_element"] * K, dict(rec, file="profiles/" + name)
+        except Exception:
+            continue
+    return None, None
 
 
 def alg_counts(mesh, v0_zero):
@@ -206,9 +207,12 @@ def time_reference(pkg, order, v0, steps, sample_cells=8):
                 return time.perf_counter() - t0
 
             t1 = run(1)
+            if t1 > 45.0:  # slow host: keep the whole measurement within a few minutes
+                steps = 1
             t2 = run(1 + steps)
         sec = max(t2 - t1, 1e-9)
-        return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "reference",
+        sample = f"cube {sample_cells}^3x6 = {K} tets, order {order}, {steps} RK4 steps"
+        return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "reference", "steps": steps,
                 "sample": sample + " (reference sources on Gmsh/Eigen stand-ins; set-up removed by differencing)", "seconds": sec}
     from oracle.oracle_py import Oracle
     mesh1.set_physics(c0=343.0, rho0=1.225, v0=v0, dt=dt)
@@ -218,8 +222,65 @@ def time_reference(pkg, order, v0, steps, sample_cells=8):
     t0 = time.perf_counter()
     orc.run(Oracle.FAITHFUL, pkg.RUNGE_KUTTA, u, 0.0, steps)
     sec = time.perf_counter() - t0
-    return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": 4.0 * K * Np * 4 * steps / sec, "unit": UNIT, "cores": cores, "kind": "port", "steps": steps,
             "sample": sample + " (oracle, faithful mode)", "seconds": sec}
+
+
+def multi_gpu_parity(pkg, torch, dist, args, rank, world):
+    """Small fixed sub-case run partitioned over all ranks (same kernel, same exchange as the timed run) and, on rank 0, on one
+    GPU: relative L2 difference per field of the merged state after 12 RK4 steps with a source running. Collective."""
+    import ctypes as C
+    n, steps = args.parity_cells, 12
+    model = pkg.Model.make_cube(n, -10.0, 10.0, args.order)
+    cfg = pkg.Config()
+    cfg.add_initial_condition(1.0, -2.0, 0.5, 30.0, 1.0)
+    cfg.add_source(2.0, 1.0, 0.0, 6.0, 10.0, 1500.0, 0.0, 1.0)
+    mesh = pkg.Mesh(model, cfg)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=args.v0, dt=0.1 * mesh.h_min() / (343.0 * (2 * args.order + 1)))
+    b = np.nonzero(mesh.fIsBoundary)[0]
+    mesh.fBC[b[::3]] = 1  # mixed absorbing / reflecting walls
+    part = np.zeros(mesh.K, dtype=np.int32)
+    fn = pkg.load_front().dgf_partition_metis if args.partitioner == "metis" else pkg.load_front().dgf_partition_rcb
+    rc = fn(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32)), None) if args.partitioner == "metis" else fn(mesh.h, world, part.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+    if args.exchange is not None:
+        eng.set_option("exchange", args.exchange)
+    if args.kernel:
+        eng.set_option("kernel", args.kernel)
+    eng.set_sources_from_config()
+    u0 = mesh.initial_condition()
+    eng.set_state(u0)
+    t_half = eng.run(pkg.RUNGE_KUTTA, 0.0, steps // 2)
+    eng.run(pkg.RUNGE_KUTTA, t_half, steps - steps // 2)
+    got = np.zeros((4, mesh.N))
+    eng.get_state(got)
+    owned = np.repeat(part == rank, mesh.Np)
+    got[:, ~owned] = 0.0
+    exchange, kernel = eng.get_option("exchange"), eng.kernel_name
+    dist.barrier()
+    eng.close()
+    merged = torch.from_numpy(got).cuda()
+    dist.all_reduce(merged)  # every DG node is owned by exactly one rank
+    out = None
+    if rank == 0:
+        single = pkg.Engine(mesh, options={"kernel": args.kernel} if args.kernel else None)
+        single.set_sources_from_config()
+        single.set_state(u0)
+        t_half = single.run(pkg.RUNGE_KUTTA, 0.0, steps // 2)
+        single.run(pkg.RUNGE_KUTTA, t_half, steps - steps // 2)
+        ref = single.get_state()
+        single.close()
+        m = merged.cpu().numpy()
+        rel = [float(np.linalg.norm(m[q] - ref[q]) / max(np.linalg.norm(ref[q]), 1e-300)) for q in range(4)]
+        out = {"rel_l2_vs_single": max(rel), "per_field": rel, "case": f"cube n={n} ({mesh.K} tets) order {args.order}, {steps} RK4 steps, source + mixed walls, "
+               f"{world} ranks ({args.partitioner}) vs 1 GPU", "kernel": kernel, "exchange": exchange, "tolerance": 1e-12}
+    dist.barrier()
+    return out
 
 
 def main():
@@ -237,9 +298,11 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--overlap", type=int, default=None, help="halo exchange overlap mode 0/1/2 (default: the engine's)")
     ap.add_argument("--sm-reserve", type=int, default=None, help="SMs left to the halo-exchange kernels during overlapped launches")
-    ap.add_argument("--exchange", type=int, default=None, help="halo exchange: 0 ncclSend/ncclRecv, 1 direct peer-to-peer stores (default: the engine's)")
+    ap.add_argument("--exchange", type=int, default=None, help="halo exchange: 0 ncclSend/ncclRecv, 1 direct peer-to-peer stores, 2 stores fused into the stage kernel (default: the engine's)")
+    ap.add_argument("--parity-cells", type=int, default=12, help="--gpus > 1: size of the partitioned-vs-single-GPU parity case reported beside the timing (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=3, help="RK4 steps of the reference's bounded sample (set-up removed by differencing against a 1-step run)")
+    ap.add_argument("--ref-cells", type=int, default=12, help="cube size n (n^3 x 6 tetrahedra) of the reference's bounded sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -261,14 +324,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, args.steps)
+        # The reference's own CPU implementation on a BOUNDED sample of the workload: a cube of --ref-cells^3 x 6 tetrahedra of
+        # the same order, physics and generator (the full 1.43 M-tetrahedron mesh would take the reference ~50 min per step
+        # and its O(F^2) set-up never finishes). `steps` / `warmup` report what actually ran.
         t0 = time.perf_counter()
-        res = None
-        for _ in range(max(1, min(args.warmup, 1))):
-            res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
+        res = time_reference(pkg, args.order, args.v0, args.cpu_steps, sample_cells=args.ref_cells)
         wall = time.perf_counter() - t0
-        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-                "ms_per_step": res["seconds"] / args.cpu_steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        config = dict(config, sample=res["sample"], sample_cells=args.ref_cells,
+                      note="throughput (DOF-updates/s) of the reference is size-independent beyond cache; the Gmsh stand-in's tetrahedron rule has "
+                           "(p+1)^3 = 125 points at order 4 where Gmsh's own degree-8 rule has ~43: the reference spends ~2.9x more time in "
+                           "getElStiffVector here than with real Gmsh")
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": res["steps"], "warmup": 1,
+                "ms_per_step": res["seconds"] / res["steps"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -320,13 +387,15 @@ def main():
             eng.set_option("sm_reserve", args.sm_reserve)
         if args.exchange is not None:
             eng.set_option("exchange", args.exchange)
-            config["exchange"] = "p2p" if args.exchange else "nccl"
     else:
         eng = pkg.Engine(mesh)
     if args.bb_tile:
         eng.set_option("bb_tile", args.bb_tile)
     if args.kernel:
         eng.set_option("kernel", args.kernel)
+    if world > 1:
+        config["exchange"] = {0: "nccl send/recv", 1: "direct peer-to-peer stores (3 launches per stage)",
+                              2: "direct peer-to-peer stores fused into the stage kernel"}[eng.get_option("exchange")]
 
     # pinned host buffers for the end-to-end leg
     host_u = torch.empty((4, mesh.N), dtype=torch.float64, pin_memory=True)
@@ -362,6 +431,10 @@ def main():
     e2e_value = unknowns * 4.0 * args.steps / e2e_s
     state_bytes = unknowns * 8
 
+    parity = None
+    if world > 1 and args.parity_cells > 0:
+        parity = multi_gpu_parity(pkg, torch, dist, args, rank, world)
+
     if rank == 0:
         peaks, how = measured_peaks()
         v0_zero = all(v == 0.0 for v in args.v0)
@@ -389,8 +462,10 @@ def main():
                                   "peak_source": "profiles/microbench/r01_fp64_peaks_b200.txt (DMMA m8n8k4 sustained)"}},
             "clocks": clk.summary(),
         }
+        if parity is not None:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            res = time_reference(pkg, args.order, args.v0, args.cpu_steps)
+            res = time_reference(pkg, args.order, args.v0, args.cpu_steps, sample_cells=args.ref_cells)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     eng.close()

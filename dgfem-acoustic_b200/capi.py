@@ -366,6 +366,7 @@ def load_dgb():
     lib.dgb_launch_count.restype = C.c_int64
     lib.dgb_launch_count.argtypes = [C.c_void_p]
     lib.dgb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.dgb_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     _dgb = lib
     return lib
 
@@ -395,6 +396,11 @@ class Engine:
 
     def set_option(self, key, value):
         self._check(self.lib.dgb_set_option(self.h, key.encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int(0)
+        self._check(self.lib.dgb_get_option(self.h, key.encode(), C.byref(v)))
+        return v.value
 
     @property
     def kernel_name(self):

@@ -203,7 +203,7 @@ struct dgb_handle {
     bool snapPending = false;
     // direct peer-to-peer halo exchange (dgb_set_option("exchange", 1), halo_p2p.cu): U / YA / YB and the epoch flags live in
     // ONE allocation ("arena") that every peer maps through CUDA IPC
-    int exchangeMode = 0;            // 0: ncclSend/ncclRecv, 1: stores into the peers' halo slots + epoch flags
+    int exchangeMode = 0;            // 0: ncclSend/ncclRecv, 1: stores into the peers' halo slots + epoch flags, 2: the same fused into the stage kernel
     char* arena = nullptr;           // owns U, YA, YB once P2P is set up
     double* phys[3] = {nullptr, nullptr, nullptr};  // allocation identity of the three exchanged arrays (the names U/YA swap in Euler runs)
     struct PeerMap { void* opened = nullptr; char* base = nullptr; int64_t stride = 0; size_t arrayBytes = 0, flagOffset = 0; };
@@ -213,6 +213,12 @@ struct dgb_handle {
     unsigned long long epoch = 0;
     int32_t *dSendPeer = nullptr, *dSendSlot = nullptr;
     int* p2pErr = nullptr;           // pinned + mapped: the wait kernel reports a timeout here
+    // exchange fused into the stage kernel (exchange = 2, stage_bb2.cu)
+    int32_t *dPushOff = nullptr, *dPushPeer = nullptr, *dPushSlot = nullptr;
+    unsigned int* dDone = nullptr;
+    FusedHalo hostFused{};
+    FusedHalo* dFused = nullptr;
+    bool haloInFlight = false;       // a fused stage has been launched whose incoming halo has not been waited for by a wait kernel
     int p2pTimeoutMs = 20000;
 };
 
@@ -253,7 +259,7 @@ void freeHandle(dgb_handle* h) {
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
     for (void* p : h->curvedAllocs) F(p);
-    F(h->dSendPeer); F(h->dSendSlot); F(h->dV); F(h->dVinv); F(h->dVC); F(h->dVinvC); F(h->dBBTab); F(h->dProbeWBB2); F(h->dRecvWBB2); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
+    F(h->dSendPeer); F(h->dSendSlot); F(h->dPushOff); F(h->dPushPeer); F(h->dPushSlot); F(h->dDone); F(h->dFused); F(h->dV); F(h->dVinv); F(h->dVC); F(h->dVinvC); F(h->dBBTab); F(h->dProbeWBB2); F(h->dRecvWBB2); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -355,6 +361,7 @@ HostOperators buildOperators(const dgb_desc* d) {
 }
 
 int representationOf(const dgb_handle* h, const StageKernel& k);
+bool setupP2P(dgb_handle* h, bool required);
 
 void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, const void* ncclId, dgb_handle** out) {
     if (!out) throw DgbException(DGB_ERR_ARG, "out is null");
@@ -610,6 +617,11 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
             NCCL_CHECK(nccl().CommInitRank(&h->comm, nranks, id, rank));
             h->sendBuf = devAlloc<double>((size_t)4 * P.sendElems.size() * Np);
             h->dSendElems = devUpload(P.sendElems);
+            // Default exchange: direct peer-to-peer stores, fused into the stage kernel where the kernel supports it, if every
+            // rank can map its peers' state arrays (CUDA IPC); otherwise NCCL send/recv. DGB_EXCHANGE=0/1/2 overrides.
+            int want = 2;
+            if (const char* e = getenv("DGB_EXCHANGE")) want = std::max(0, std::min(2, atoi(e)));
+            if (want >= 1 && setupP2P(h, false)) h->exchangeMode = want;
         }
         *out = h;
     } catch (...) {
@@ -628,6 +640,7 @@ void launchStage(dgb_handle* h, StageArgs A, int eBegin, int eEnd, bool timed) {
     A.eBegin = eBegin;
     A.eEnd = eEnd;
     A.smReserve = (h->partitioned && h->exchangeMode == 0 && overlapMode(h) && eEnd <= h->plan.Kinterior) ? h->smReserve : 0;  // interior launches beside NCCL kernels only
+    if (A.fx == nullptr) { A.fxWhich = 0; A.fxEpochWait = A.fxEpochSignal = 0; }
     const bool t = timed && h->timeStages && h->stageEvUsed + 2 <= (int)h->stageEv.size();
     if (t) cudaEventRecord(h->stageEv[h->stageEvUsed], h->stream);
     int nLaunched = 1;
@@ -687,31 +700,44 @@ struct P2PRecord {
     int32_t slot0[MAX_PEERS];  // [r] first local element slot of rank r's halo elements (-1: not a peer)
     int32_t count[MAX_PEERS];  // [r] number of halo elements expected from rank r
     int32_t device;
+    int32_t ok;          // this rank got as far as the record describes
 };
 
-void setupP2P(dgb_handle* h) {
-    if (!h->partitioned) throw DgbException(DGB_ERR_UNSUPPORTED, "exchange = 1 needs a partitioned handle");
-    if (!h->peerMap.empty() || h->arena) return;
-    if (h->nranks > MAX_PEERS) throw DgbException(DGB_ERR_UNSUPPORTED, "direct exchange supports at most 16 ranks");
+// Returns false (after undoing everything, on every rank alike) if some rank cannot take part — no CUDA IPC in this
+// environment, no memory for the arena — so that the caller can fall back to NCCL; throws if `required`. Every rank makes
+// the same sequence of collective calls whatever happens locally.
+bool setupP2P(dgb_handle* h, bool required) {
+    if (!h->partitioned) throw DgbException(DGB_ERR_UNSUPPORTED, "exchange = 1 / 2 needs a partitioned handle");
+    if (!h->peerMap.empty() || h->arena) return true;
+    if (h->nranks > MAX_PEERS) {
+        if (required) throw DgbException(DGB_ERR_UNSUPPORTED, "direct exchange supports at most 16 ranks");
+        return false;
+    }
     const PartitionPlan& P = h->plan;
     const int rank = P.rank, nranks = h->nranks;
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     if (h->commStream) CUDA_CHECK(cudaStreamSynchronize(h->commStream));
-    // 1. arena: three state arrays (256-byte aligned) + one flag per rank
+    // 1. arena: three state arrays (256-byte aligned) + one flag per rank — local work, failures are recorded, not thrown
     const size_t stateBytes = (size_t)4 * h->M.stride * sizeof(double);
     const size_t arrBytes = (stateBytes + 255) / 256 * 256;
     const size_t flagOff = 3 * arrBytes, total = flagOff + 256;
     char* arena = nullptr;
-    CUDA_CHECK(cudaMalloc(&arena, total));
-    CUDA_CHECK(cudaMemset(arena, 0, total));
     double* old[3] = {h->U, h->YA, h->YB};
-    for (int k = 0; k < 3; ++k) CUDA_CHECK(cudaMemcpy(arena + k * arrBytes, old[k], stateBytes, cudaMemcpyDeviceToDevice));
-    // 2. publish
     std::vector<P2PRecord> rec(nranks);
     P2PRecord& me = rec[rank];
     std::memset(&me, 0, sizeof(me));
-    CUDA_CHECK(cudaIpcGetMemHandle(&me.mem, arena));
-    {
+    std::string why;
+    try {
+        CUDA_CHECK(cudaMalloc(&arena, total));
+        CUDA_CHECK(cudaMemset(arena, 0, total));
+        for (int k = 0; k < 3; ++k) CUDA_CHECK(cudaMemcpy(arena + k * arrBytes, old[k], stateBytes, cudaMemcpyDeviceToDevice));
+        CUDA_CHECK(cudaIpcGetMemHandle(&me.mem, arena));
+        me.ok = 1;
+    } catch (const DgbException& e) {
+        why = e.what();
+        cudaGetLastError();
+    }
+    if (me.ok) {
         // offset of the arena inside the allocation the handle names (cudaMalloc may sub-allocate small requests)
         typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
         void* fn = nullptr;
@@ -733,21 +759,37 @@ void setupP2P(dgb_handle* h) {
         me.count[P.peers[i]] = P.recvOffset[i + 1] - P.recvOffset[i];
     }
     CUDA_CHECK(cudaGetDevice(&me.device));
+    // 2. publish (every rank, whatever happened above)
     P2PRecord* dRec = devAlloc<P2PRecord>(nranks);
-    try {
+    auto gather = [&]() {
         CUDA_CHECK(cudaMemcpy(dRec + rank, &me, sizeof(me), cudaMemcpyHostToDevice));
         NCCL_CHECK(nccl().AllGather(dRec + rank, dRec, sizeof(P2PRecord), ncclChar, h->comm, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         CUDA_CHECK(cudaMemcpy(rec.data(), dRec, sizeof(P2PRecord) * nranks, cudaMemcpyDeviceToHost));
-    } catch (...) {
+    };
+    auto allOk = [&]() { for (int r = 0; r < nranks; ++r) if (!rec[r].ok) return false; return true; };
+    std::vector<dgb_handle::PeerMap> maps(P.peers.size());
+    auto undo = [&]() {
+        for (auto& pm : maps) if (pm.opened) { cudaIpcCloseMemHandle(pm.opened); pm.opened = nullptr; }
+        if (arena) cudaFree(arena);
+        arena = nullptr;
         cudaFree(dRec);
-        cudaFree(arena);
+        cudaGetLastError();
+    };
+    try {
+        gather();
+    } catch (...) {
+        undo();
         throw;
     }
-    cudaFree(dRec);
-    // 3. map the peers
-    std::vector<dgb_handle::PeerMap> maps(P.peers.size());
+    if (!allOk()) {
+        undo();
+        if (required) throw DgbException(DGB_ERR_UNSUPPORTED, "direct exchange unavailable: " + (why.empty() ? std::string("a peer could not export its state arrays") : why));
+        return false;
+    }
+    // 3. map the peers; a failure is again agreed on collectively
     std::vector<int32_t> sendPeer(P.sendElems.size()), sendSlot(P.sendElems.size());
+    P2PRecord mine = me;
     try {
         for (size_t i = 0; i < P.peers.size(); ++i) {
             const P2PRecord& pr = rec[P.peers[i]];
@@ -762,15 +804,28 @@ void setupP2P(dgb_handle* h) {
             if (pr.arrayBytes != expect || pr.flagOffset != 3 * pr.arrayBytes) throw DgbException(DGB_ERR_STATE, "direct exchange: inconsistent arena layout");
             for (int k = P.sendOffset[i]; k < P.sendOffset[i + 1]; ++k) { sendPeer[k] = (int32_t)i; sendSlot[k] = pr.slot0[rank] + (k - P.sendOffset[i]); }
         }
-        h->dSendPeer = devUpload(sendPeer);
-        h->dSendSlot = devUpload(sendSlot);
-        CUDA_CHECK(cudaHostAlloc(&h->p2pErr, sizeof(int), cudaHostAllocMapped));
-        *h->p2pErr = 0;
+    } catch (const DgbException& e) {
+        why = e.what();
+        mine.ok = 0;
+        cudaGetLastError();
+    }
+    me = mine;
+    try {
+        gather();
     } catch (...) {
-        for (auto& pm : maps) if (pm.opened) cudaIpcCloseMemHandle(pm.opened);
-        cudaFree(arena);
+        undo();
         throw;
     }
+    if (!allOk()) {
+        undo();
+        if (required) throw DgbException(DGB_ERR_UNSUPPORTED, "direct exchange unavailable: " + (why.empty() ? std::string("a peer could not map this rank's state arrays") : why));
+        return false;
+    }
+    cudaFree(dRec);
+    h->dSendPeer = devUpload(sendPeer);
+    h->dSendSlot = devUpload(sendSlot);
+    CUDA_CHECK(cudaHostAlloc(&h->p2pErr, sizeof(int), cudaHostAllocMapped));
+    *h->p2pErr = 0;
     // 4. commit: the arena replaces the three separate arrays
     for (int k = 0; k < 3; ++k) cudaFree(old[k]);
     h->arena = arena;
@@ -782,6 +837,46 @@ void setupP2P(dgb_handle* h) {
     h->dFlags = reinterpret_cast<unsigned long long*>(arena + flagOff);
     h->peerMap.swap(maps);
     h->epoch = 0;
+    // 5. tables of the exchange fused into the stage kernel (exchange = 2)
+    {
+        const int nBorder = P.Kown - P.Kinterior;
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> targets(nBorder);
+        for (size_t k = 0; k < P.sendElems.size(); ++k) {
+            const int b = P.sendElems[k] - P.Kinterior;
+            if (b < 0 || b >= nBorder) throw DgbException(DGB_ERR_STATE, "direct exchange: a send element is not a border element");
+            targets[b].push_back({sendPeer[k], sendSlot[k]});
+        }
+        std::vector<int32_t> off(nBorder + 1, 0), pp, ps;
+        for (int b = 0; b < nBorder; ++b) {
+            for (auto& t : targets[b]) { pp.push_back(t.first); ps.push_back(t.second); }
+            off[b + 1] = (int32_t)pp.size();
+        }
+        h->dPushOff = devUpload(off);
+        h->dPushPeer = devUpload(pp);
+        h->dPushSlot = devUpload(ps);
+        h->dDone = devAlloc<unsigned int>(1);
+        CUDA_CHECK(cudaMemset(h->dDone, 0, sizeof(unsigned int)));
+        FusedHalo F{};
+        F.Kinterior = P.Kinterior;
+        F.nPeers = (int)P.peers.size();
+        F.pushOff = h->dPushOff; F.pushPeer = h->dPushPeer; F.pushSlot = h->dPushSlot;
+        for (size_t i = 0; i < P.peers.size(); ++i) {
+            const dgb_handle::PeerMap& pm = h->peerMap[i];
+            for (int k = 0; k < 3; ++k) F.arr[k][i] = reinterpret_cast<double*>(pm.base + (size_t)k * pm.arrayBytes);
+            F.peerFlag[i] = reinterpret_cast<unsigned long long*>(pm.base + pm.flagOffset) + P.rank;
+            F.waitRank[i] = P.peers[i];
+        }
+        F.myFlags = h->dFlags;
+        F.doneCounter = h->dDone;
+        F.timeoutNs = (unsigned long long)h->p2pTimeoutMs * 1000000ull;
+        int* errDev = nullptr;
+        CUDA_CHECK(cudaHostGetDevicePointer(&errDev, h->p2pErr, 0));
+        F.err = errDev;
+        h->hostFused = F;
+        h->dFused = devAlloc<FusedHalo>(1);
+        CUDA_CHECK(cudaMemcpy(h->dFused, &F, sizeof(F), cudaMemcpyHostToDevice));
+    }
+    return true;
 }
 
 // push the owned cut-adjacent elements of `produced` into the peers' halo slots and raise this rank's flag there
@@ -818,7 +913,7 @@ void waitHalo(dgb_handle* h) {
 // second, small launch per stage (prologue, pipeline fill / drain, static tile lists) than the ~0.09 ms exchange costs, at 2, 4
 // and 8 GPUs alike, so they run one launch per stage and exchange afterwards; the light-weight generic kernel overlaps.
 int overlapMode(const dgb_handle* h) {
-    if (h->exchangeMode == 1) return h->overlap >= 1 ? 1 : h->overlap == 0 ? 0 : (h->active.launch == h->generic.launch ? 1 : 0);  // no deferred order
+    if (h->exchangeMode >= 1) return h->overlap >= 1 ? 1 : h->overlap == 0 ? 0 : (h->active.launch == h->generic.launch ? 1 : 0);  // no deferred order
     if (h->overlap >= 0) return h->overlap;
     return h->active.launch == h->generic.launch ? 1 : 0;
 }
@@ -838,7 +933,23 @@ void runStage(dgb_handle* h, const StageArgs& A, double* produced) {
     }
     const int nSendEl = (int)P.sendElems.size();
     const int overlap = overlapMode(h);
-    if (h->exchangeMode == 1) {
+    if (h->exchangeMode == 2 && h->active.launch == h->bb2Kernel.launch) {
+        // exchange fused into the stage kernel: one launch over all owned elements; the border tiles (last in the interior-first
+        // numbering) wait for the peers' flags of the previous stage, push their results into the peers' halo slots, and the
+        // last CTA signals. Nothing else is launched.
+        int which = -1;
+        for (int k = 0; k < 3; ++k) if (produced == h->phys[k]) which = k;
+        if (which < 0) throw DgbException(DGB_ERR_STATE, "direct exchange: produced array is not one of the exchanged arrays");
+        StageArgs B = A;
+        B.fx = h->dFused;
+        B.fxWhich = which;
+        B.fxEpochWait = h->epoch;
+        B.fxEpochSignal = ++h->epoch;
+        launchStage(h, B, 0, h->M.Kown, true);
+        h->haloInFlight = true;
+        return;
+    }
+    if (h->exchangeMode >= 1) {
         // direct stores into the peers' halo slots: the transfer needs no second stream, it drains over NVLink while the
         // interior elements run (overlap 1) or is simply waited for (overlap 0)
         if (overlap == 1) {
@@ -889,6 +1000,10 @@ void finishExchange(dgb_handle* h) {
     if (h->recvPending) {
         CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->evRecv, 0));
         h->recvPending = false;
+    }
+    if (h->haloInFlight) {  // fused exchange: the peers' pushes of the last stage are awaited by the next stage kernel; here by a wait kernel
+        waitHalo(h);
+        h->haloInFlight = false;
     }
 }
 
@@ -1479,11 +1594,19 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             h->overlap = value;
         }
         else if (k == "exchange") {  // collective: every rank of the communicator must make the same call
-            if (value != 0 && value != 1) throw DgbException(DGB_ERR_ARG, "exchange must be 0 (NCCL send/recv) or 1 (direct peer-to-peer stores)");
+            if (value < 0 || value > 2)
+                throw DgbException(DGB_ERR_ARG, "exchange must be 0 (NCCL send/recv), 1 (direct peer-to-peer stores) or 2 (stores fused into the stage kernel)");
             finishExchange(h);
-            if (value == 1) setupP2P(h);
+            if (value >= 1) setupP2P(h, true);
             h->exchangeMode = value;
-        } else if (k == "p2p_timeout_ms") h->p2pTimeoutMs = std::max(1, value);
+        } else if (k == "p2p_timeout_ms") {
+            h->p2pTimeoutMs = std::max(1, value);
+            if (h->dFused) {
+                h->hostFused.timeoutNs = (unsigned long long)h->p2pTimeoutMs * 1000000ull;
+                CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                CUDA_CHECK(cudaMemcpy(h->dFused, &h->hostFused, sizeof(FusedHalo), cudaMemcpyHostToDevice));
+            }
+        }
         else if (k == "bb_tile") {  // elements per CTA of the Bernstein kernels; takes effect at once if one of them is active
             if (value != 8 && value != 16 && value != 32) throw DgbException(DGB_ERR_ARG, "bb_tile must be 8, 16 or 32");
             if (h->bbKernel.launch) {
@@ -1498,6 +1621,23 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
         else if (k == "sm_reserve") h->smReserve = std::max(0, value);
         else if (k == "graph") h->useGraph = value < 0 ? -1 : (value ? 1 : 0);
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;
+        else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
+    });
+}
+
+int dgb_get_option(dgb_handle* h, const char* key, int* value) {
+    return guarded([&] {
+        if (!h || !key || !value) throw DgbException(DGB_ERR_ARG, "null argument");
+        const std::string k(key);
+        auto is = [&](const StageKernel& s) { return s.launch && h->active.launch == s.launch; };
+        if (k == "kernel") *value = is(h->bb2Kernel) ? 6 : is(h->bbSeqKernel) ? 5 : is(h->bbKernel) ? 4 : is(h->ws) ? 3 : is(h->tiled) ? 2 : 1;
+        else if (k == "exchange") *value = h->partitioned ? h->exchangeMode : 0;
+        else if (k == "representation") *value = h->bbMode;
+        else if (k == "overlap") *value = h->partitioned ? overlapMode(h) : 0;
+        else if (k == "graph") *value = h->useGraph;
+        else if (k == "bb_tile") *value = h->bbTile;
+        else if (k == "sm_reserve") *value = h->smReserve;
+        else if (k == "p2p_timeout_ms") *value = h->p2pTimeoutMs;
         else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
     });
 }

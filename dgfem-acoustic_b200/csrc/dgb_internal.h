@@ -53,6 +53,25 @@ struct DeviceMesh {
     uint8_t bbOwn[4][28];  // the first table again, in the kernel's parameter space (uniform run-time index)
 };
 
+constexpr int MAX_PEERS = 16;
+// Halo exchange fused into the stage kernel (stage_bb2.cu, dgb_set_option("exchange", 2)): device-resident tables of a
+// partitioned handle. The kernel stores the results of its cut-adjacent elements straight into the peers' halo slots
+// (CUDA IPC mappings of the peers' state arrays), the last CTA raises this rank's epoch flag at every peer, and the tiles
+// that read halo values wait for the peers' flags of the previous stage.
+struct FusedHalo {
+    int Kinterior, nPeers;
+    const int32_t* pushOff;    // [Kown - Kinterior + 1] range of (peer, slot) targets of border element Kinterior + k
+    const int32_t* pushPeer;   // index into the peer tables below
+    const int32_t* pushSlot;   // element slot in that peer's arrays
+    double* arr[3][MAX_PEERS];                 // the peers' copies of the three exchanged arrays (U, YA, YB by allocation)
+    unsigned long long* peerFlag[MAX_PEERS];   // this rank's slot in each peer's flag array
+    const unsigned long long* myFlags;         // this rank's flag array, indexed by rank
+    int waitRank[MAX_PEERS];
+    unsigned int* doneCounter;                 // CTAs that have finished (and whose pushes are complete) in the running launch
+    unsigned long long timeoutNs;
+    int* err;                                  // pinned + mapped: 1 + rank of a peer that never signalled
+};
+
 struct StageArgs {
     const double* yin;   // stage input  [4][stride]
     double* u;           // solution     [4][stride]
@@ -62,6 +81,9 @@ struct StageArgs {
     int mode;
     double dt;
     int smReserve;       // persistent kernels leave this many SMs free (halo exchange kernels running beside an interior launch)
+    const FusedHalo* fx;                         // fused halo exchange (nullptr: none)
+    int fxWhich;                                 // which of the three exchanged arrays this launch produces
+    unsigned long long fxEpochWait, fxEpochSignal;
 };
 
 // Returns a printable kernel name; launches on `stream`. kernelChoice: 0 auto, 1 generic, 2 tiled.
@@ -100,7 +122,6 @@ void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* 
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
 
 // direct peer-to-peer halo exchange (halo_p2p.cu); tables are passed by value as kernel arguments
-constexpr int MAX_PEERS = 16;
 struct PeerTargets { double* arr[MAX_PEERS]; long long stride[MAX_PEERS]; };   // the peers' copy of the produced array, [4][stride]
 struct PeerFlags { unsigned long long* flag[MAX_PEERS]; int n; };              // THIS rank's slot in each peer's flag array
 struct PeerWait { int rank[MAX_PEERS]; int n; };                               // ranks whose flags this rank waits for

@@ -149,6 +149,33 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     const double* const uSrc = mode == MODE_EULER ? A.yin : A.u;  // first RK stage: u is the stage input (an L2 hit)
     double* const uDst = mode == MODE_RK4 ? A.u : A.yout;
 
+    // fused halo exchange (partitioned handles): the tiles that hold cut-adjacent elements come last (interior-first
+    // numbering); they read halo values — wait for the peers' flags of the previous stage first — and their results go
+    // straight into the peers' halo slots
+    const FusedHalo* const fx = A.fx;
+    bool haloReady = fx == nullptr;
+    auto touchesBorder = [&](int tt) { return A.eBegin + (tt + 1) * kTE2 > fx->Kinterior; };
+    auto waitPeers = [&]() {
+        if (lane < fx->nPeers) {
+            const unsigned long long* f = fx->myFlags + fx->waitRank[lane];
+            unsigned long long t0, t1, v;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v >= A.fxEpochWait) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > fx->timeoutNs) {
+                    *fx->err = 1 + fx->waitRank[lane];
+                    __threadfence_system();
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncwarp();
+        haloReady = true;
+    };
+
     int t = blockIdx.x;
     if (t >= nTiles) return;
     if (lane == 0) {
@@ -205,6 +232,7 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     if (lane == 0) issueY(t);
     sMeta[lane] = make_int2(flags, nbr);
     __syncwarp();
+    if (!haloReady && touchesBorder(t)) waitPeers();
     issueTraces(0, sMeta);
     uint32_t phY = 0, phU = 0, phA = 0;
     int mb = 0;  // which half of sMeta holds this tile
@@ -297,6 +325,7 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
                 if (more) {
                     metaN[lane] = make_int2(flagsN, nbrN);
                     __syncwarp();
+                    if (!haloReady && touchesBorder(tn)) waitPeers();
                     issueTraces(0, metaN);
                 }
             }
@@ -350,10 +379,23 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
             bulkStore(uDst + (int64_t)e0 * NP * 4, sY, bytes);
             if (storeA) bulkStore(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
             bulkCommit();
-            if (more) {
-                bulkWaitRead();  // both tiles have been read by the stores
-                issueY(tn);
+        }
+        if (fx != nullptr && touchesBorder(t)) {
+            // lane l ships element l of the tile to every peer that holds it as a halo element: one bulk store per target,
+            // straight from the shared-memory tile over NVLink
+            const int k = e0 + lane - fx->Kinterior;
+            if (lane < (int)(bytes / (NP * 32)) && k >= 0) {
+                const int p1 = fx->pushOff[k + 1];
+                for (int p = fx->pushOff[k]; p < p1; ++p)
+                    bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sY + lane * NP * 4, NP * 32);
+                bulkCommit();
             }
+            bulkWaitRead();
+            __syncwarp();
+        }
+        if (lane == 0 && more) {
+            bulkWaitRead();  // both tiles have been read by the stores
+            issueY(tn);
         }
         if (!more) break;
         t = tn;
@@ -365,7 +407,22 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
 #pragma unroll
         for (int j = 0; j < 9; ++j) G[j] = GN[j];
     }
-    if (lane == 0) bulkWaitAll();
+    bulkWaitAll();  // every store of this warp, local and remote, is complete
+    if (fx != nullptr) {
+        // the last CTA to get here raises this rank's flag at every peer (release at system scope after all pushes)
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) {
+            __threadfence_system();
+            last = atomicAdd(fx->doneCounter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+            if (lane == 0) *fx->doneCounter = 0;
+            __threadfence_system();
+            if (lane < fx->nPeers) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fx->peerFlag[lane]), "l"(A.fxEpochSignal) : "memory");
+        }
+    }
 }
 
 template <int P>

@@ -152,7 +152,27 @@ int dgb_synchronize(dgb_handle* h);
 double dgb_last_run_ms(dgb_handle* h);        /* CUDA-event time of the last dgb_run */
 double dgb_last_stage_kernel_ms(dgb_handle* h); /* mean CUDA-event duration of the stage kernel in the last run */
 int64_t dgb_launch_count(dgb_handle* h);      /* kernels launched by this handle so far */
-int dgb_set_option(dgb_handle* h, const char* key, int value); /* "kernel": 0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow), 4 / 5 Bernstein-Bezier sparse-operator kernel for tetrahedra of order 2..5 (the state is then kept as Bernstein coefficients on the device; 5 = face-sequential schedule; "bb_tile": 32 / 16 / 8 elements per CTA of those kernels); "overlap": -1 automatic (default), 0 none, 1 same-stage, 2 next-stage; "sm_reserve": SMs left to NCCL during overlapped launches; "exchange" (COLLECTIVE, partitioned handles): 0 ncclSend/ncclRecv (default), 1 direct stores into the peers' halo slots over NVLink through CUDA IPC mappings + epoch flags (csrc/halo_p2p.cu; overlap 0 / 1 only; destroy becomes collective); "p2p_timeout_ms": how long a rank waits for a peer's halo before dgb_run fails; "graph": -1 automatic / 0 / 1 CUDA graph of an RK4 step (one GPU, no sources / probes / receivers); "time_stages": 0/1 */
+/* Options (all integers):
+ *   "kernel"   0 automatic (default: the second-generation Bernstein-Bezier kernel for tetrahedra of order >= 3, else the
+ *              CUDA-core kernel), 1 generic CUDA cores, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow),
+ *              4 / 5 first-generation Bernstein-Bezier kernels (tetrahedra of order 2..5; 5 = face-sequential schedule;
+ *              "bb_tile": 32 / 16 / 8 elements per CTA), 6 second-generation Bernstein-Bezier kernel (csrc/stage_bb2.cu).
+ *              With a Bernstein kernel the state is kept as Bernstein coefficients on the device; dgb_set_state /
+ *              dgb_get_state / probes / receivers / sources convert.
+ *   "overlap"  -1 automatic (default), 0 none, 1 same-stage, 2 next-stage (NCCL exchange only)
+ *   "sm_reserve" SMs left to NCCL during overlapped launches
+ *   "exchange" (COLLECTIVE, partitioned handles) 0 ncclSend/ncclRecv; 1 direct stores into the peers' halo slots over NVLink
+ *              through CUDA IPC mappings + epoch flags (csrc/halo_p2p.cu: three small launches per stage); 2 the same stores
+ *              issued by the stage kernel itself (TMA bulk stores from shared memory, last CTA signals, border tiles wait:
+ *              no extra launch; second-generation Bernstein kernel, other kernels behave as with 1). Default: 2 if every rank
+ *              can map its peers' arrays, else 0 (environment DGB_EXCHANGE overrides). With 1 / 2 destroy is collective.
+ *   "p2p_timeout_ms" how long a rank waits for a peer's halo before dgb_run fails
+ *   "graph"    -1 automatic / 0 / 1 CUDA graph of an RK4 step (one GPU, no sources / probes / receivers)
+ *   "time_stages" 0 / 1 */
+int dgb_set_option(dgb_handle* h, const char* key, int value);
+/* Reads back an option ("kernel" reports the active kernel's id, "exchange" the mode in effect, "representation" 0 nodal /
+ * 1 / 2 Bernstein layouts, "overlap", "graph", "bb_tile", "sm_reserve", "p2p_timeout_ms"). */
+int dgb_get_option(dgb_handle* h, const char* key, int* value);
 const char* dgb_kernel_name(dgb_handle* h);   /* which stage kernel the handle selected */
 const char* dgb_last_error(void);
 const char* dgb_version(void);
