@@ -195,7 +195,8 @@ struct dgb_handle {
     ncclComm_t comm = nullptr;
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int32_t* dSendElems = nullptr;
-    double* hostStage = nullptr;  // pinned, [4][stride], partitioned handles only
+    double* hostStage = nullptr;  // pinned, [4][stride], partitioned handles only (pageable caller buffers)
+    int32_t* dL2G = nullptr;      // localToGlobal on the device (pinned caller buffers: the GPU gathers / scatters over PCIe)
     // asynchronous snapshot: device-side copy of the state + a copy stream
     double* dSnap = nullptr;
     cudaStream_t snapStream = nullptr;
@@ -259,7 +260,7 @@ void freeHandle(dgb_handle* h) {
     if (h->p2pErr) cudaFreeHost(h->p2pErr);
     if (h->arena) { F(h->arena); h->U = h->YA = h->YB = nullptr; }  // the arena owns the three arrays
     for (void* p : h->curvedAllocs) F(p);
-    F(h->dSendPeer); F(h->dSendSlot); F(h->dPushOff); F(h->dPushPeer); F(h->dPushSlot); F(h->dDone); F(h->dFused); F(h->dV); F(h->dVinv); F(h->dVC); F(h->dVinvC); F(h->dBBTab); F(h->dProbeWBB2); F(h->dRecvWBB2); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
+    F(h->dL2G); F(h->dSendPeer); F(h->dSendSlot); F(h->dPushOff); F(h->dPushPeer); F(h->dPushSlot); F(h->dDone); F(h->dFused); F(h->dV); F(h->dVinv); F(h->dVC); F(h->dVinvC); F(h->dBBTab); F(h->dProbeWBB2); F(h->dRecvWBB2); F(h->dProbeElBB); F(h->dProbeWBB); F(h->dRecvWBB); F(h->dSrcElList); F(h->dSrcNodeOff); F(h->dSrcNodeLocal);
     F(h->U); F(h->ACC); F(h->YA); F(h->YB);
     F(h->M.DwT); F(h->M.nLiftT); F(h->M.tiledOps); F(h->M.faceNodes); F(h->M.nbrMaps);
     F(h->M.Ginv); F(h->M.fgeo); F(h->M.fnbr); F(h->M.fflags);
@@ -1195,6 +1196,15 @@ int hostThreads(const dgb_handle* h) {
     return std::max(1, std::min(share, 16));
 }
 
+// Device-side address of a caller buffer if it is page-locked host memory (cudaMallocHost / cudaHostRegister /
+// dgb_host_alloc), nullptr for pageable memory.
+const double* deviceViewOfHost(const double* p) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+    return static_cast<const double*>(attr.devicePointer);
+}
+
 double* stagingBuffer(dgb_handle* h) {
     if (!h->hostStage) CUDA_CHECK(cudaMallocHost(&h->hostStage, (size_t)4 * h->M.stride * sizeof(double)));
     return h->hostStage;
@@ -1216,9 +1226,18 @@ void stateToDevice(dgb_handle* h, const double* u, double* dst) {
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         return;
     }
+    const int Ktot = h->M.Ktot;
+    if (const double* mapped = deviceViewOfHost(u)) {  // pinned caller buffer: the GPU reads it directly, element by element
+        if (!h->dL2G) h->dL2G = devUpload(h->plan.localToGlobal);
+        launchGatherState(mapped, Ng, h->dL2G, Ktot, Np, h->bbMode == 2 ? h->ACC : dst, S, h->stream);
+        ++h->launches;
+        if (h->bbMode == 2) { launchConvertBB2(h->ACC, dst, S, Np, Ktot, h->dVinvC, true, h->stream); ++h->launches; }
+        else if (h->bbMode) { launchElementMatrix(dst, dst, S, Np, Ktot, h->dVinv, h->stream); ++h->launches; }
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        return;
+    }
     double* stage = stagingBuffer(h);
     const int32_t* l2g = h->plan.localToGlobal.data();
-    const int Ktot = h->M.Ktot;
     const int nth = hostThreads(h);
     // field by field: the copy of field q runs while field q+1 is gathered
     for (int q = 0; q < 4; ++q) {
@@ -1246,9 +1265,16 @@ void stateToHost(dgb_handle* h, const double* src, double* u) {
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         return;
     }
+    const int Kown = h->M.Kown;
+    if (double* mapped = const_cast<double*>(deviceViewOfHost(u))) {  // pinned caller buffer: the GPU writes the owned elements into it
+        if (!h->dL2G) h->dL2G = devUpload(h->plan.localToGlobal);
+        launchScatterState(mapped, Ng, h->dL2G, Kown, Np, src, S, h->stream);
+        ++h->launches;
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        return;
+    }
     double* stage = stagingBuffer(h);
     const int32_t* l2g = h->plan.localToGlobal.data();
-    const int Kown = h->M.Kown;
     const int nth = hostThreads(h);
     cudaEvent_t ev[4];
     for (int q = 0; q < 4; ++q) {

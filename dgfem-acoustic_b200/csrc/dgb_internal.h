@@ -121,6 +121,10 @@ void launchGatherReceivers(const double* u, int64_t stride, int Np, const int32_
 void launchPackElements(const double* y, int64_t stride, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int n, const double* buf, cudaStream_t s);
 
+// partitioned handles, pinned caller buffers: gather / scatter between the caller's global array and the rank's local order (state_io.cu)
+void launchGatherState(const double* globalHost, int64_t Ng, const int32_t* l2g, int K, int Np, double* local, int64_t stride, cudaStream_t s);
+void launchScatterState(double* globalHost, int64_t Ng, const int32_t* l2g, int K, int Np, const double* local, int64_t stride, cudaStream_t s);
+
 // direct peer-to-peer halo exchange (halo_p2p.cu); tables are passed by value as kernel arguments
 struct PeerTargets { double* arr[MAX_PEERS]; long long stride[MAX_PEERS]; };   // the peers' copy of the produced array, [4][stride]
 struct PeerFlags { unsigned long long* flag[MAX_PEERS]; int n; };              // THIS rank's slot in each peer's flag array
