@@ -51,6 +51,10 @@ def main():
         eng.set_option("exchange", exchange)  # collective
     eng.set_sources_from_config()
     eng.set_probes(probes)
+    # interpolated receivers in different parts of the cube: with 2 ranks at least one lies in an element of rank 1
+    r_el, r_w = mesh.locate_receivers([(-6.3, 2.2, 1.1), (6.1, -3.3, 0.4), (0.2, 7.7, -5.1), (1.3, -8.2, 6.6)])
+    assert len(set(int(part[e]) for e in r_el)) > 1
+    eng.set_receivers(r_el, r_w)
     pinned = cells % 2 == 1  # odd sizes: page-locked caller buffers (the GPU gathers / scatters them over PCIe), even: pageable (staged)
     if pinned:
         hu, hg = torch.empty((4, mesh.N), dtype=torch.float64, pin_memory=True), torch.empty((4, mesh.N), dtype=torch.float64, pin_memory=True)
@@ -65,18 +69,20 @@ def main():
     eng.get_state(got)
     got = np.array(got)
     rec = eng.get_probes(steps)
+    rcv = eng.get_receivers(steps)
     owned = np.repeat(part == rank, mesh.Np)
-    np.savez(Path(out_dir) / f"rank{rank}.npz", u=got, owned=owned, probes=rec, launches=eng.launch_count)
+    np.savez(Path(out_dir) / f"rank{rank}.npz", u=got, owned=owned, probes=rec, receivers=rcv, launches=eng.launch_count)
     dist.barrier()
     eng.close()
     if rank == 0:
         single = pkg.Engine(mesh, options={"kernel": kernel} if kernel else None)
         single.set_sources_from_config()
         single.set_probes(probes)
+        single.set_receivers(r_el, r_w)
         single.set_state(u0)
         t_half = single.run(pkg.RUNGE_KUTTA, 0.0, steps // 2)
         single.run(pkg.RUNGE_KUTTA, t_half, steps - steps // 2)
-        np.savez(Path(out_dir) / "single.npz", u=single.get_state(), probes=single.get_probes(steps))
+        np.savez(Path(out_dir) / "single.npz", u=single.get_state(), probes=single.get_probes(steps), receivers=single.get_receivers(steps))
         single.close()
     dist.barrier()
     dist.destroy_process_group()

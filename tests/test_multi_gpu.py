@@ -54,13 +54,16 @@ def _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, ker
     merged = np.zeros_like(single["u"])
     covered = np.zeros(merged.shape[1], dtype=int)
     probes = np.zeros_like(single["probes"])
+    receivers = np.zeros_like(single["receivers"])
     for r in range(world):
         z = np.load(tmp_path / f"rank{r}.npz")
         merged[:, z["owned"]] = z["u"][:, z["owned"]]
         covered += z["owned"]
         probes += z["probes"]  # probes owned by another rank are returned as zeros
+        receivers += z["receivers"]  # likewise the receivers (at least one lies on a non-zero rank)
         assert z["launches"] > 0
     assert (covered == 1).all()
     for q in range(4):
         assert rel_l2(merged[q], single["u"][q]) < tol
         assert rel_l2(probes[:, :, q], single["probes"][:, :, q]) < tol
+        assert rel_l2(receivers[:, :, q], single["receivers"][:, :, q]) < tol
