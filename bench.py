@@ -130,11 +130,13 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def build_workload(pkg, cells, order, v0):
-    model = pkg.Model.make_cube(cells, -10.0, 10.0, order)
+def build_workload(pkg, cells, order, v0, dim=3):
+    model = pkg.Model.make_cube(cells, -10.0, 10.0, order) if dim == 3 else pkg.Model.make_square(cells, -10.0, 10.0, order)
     cfg = pkg.Config()
     cfg.add_initial_condition(0.0, 0.0, 0.0, 1.0, 1.0)  # config.conf:57
     mesh = pkg.Mesh(model, cfg)
+    if dim == 2:  # BASELINE config 2: refined square, reflecting walls
+        mesh.fBC[np.nonzero(mesh.fIsBoundary)[0]] = 1
     c0, rho0 = 343.0, 1.225
     dt = 0.1 * mesh.h_min() / (c0 * (2 * order + 1))
     mesh.set_physics(c0=c0, rho0=rho0, v0=v0, dt=dt)
@@ -156,8 +158,11 @@ def measured_traffic(kernel_name, K):
 def alg_counts(mesh, v0_zero):
     """Algorithmic bytes / flops of ONE stage launch over the whole mesh."""
     K, Np, Nfp = mesh.K, mesh.Np, mesh.Nfp
-    bytes_stage = 34.0 * 4 * K * Np + 232.0 * K
-    flops_el = (12.0 if v0_zero else 24.0) * Np * Np + 32.0 * Np * Nfp + 160.0 * Nfp + 40.0 * Np
+    d, Nf = mesh.desc.dim, mesh.desc.Nf
+    # per element: d*d inverse-Jacobian entries + per face (normal, Fscale) + 2 int32 = 232 B for a tetrahedron
+    bytes_stage = 34.0 * 4 * K * Np + (8.0 * d * d + 40.0 * Nf) * K
+    # volume: 2d matvecs (div v, grad p), 4d with mean flow; lift: 4 fields x Nf faces; flux + pointwise
+    flops_el = (4.0 if v0_zero else 8.0) * d * Np * Np + 8.0 * Nf * Np * Nfp + 40.0 * Nf * Nfp + 40.0 * Np
     return bytes_stage, flops_el * K
 
 
@@ -291,6 +296,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=62)
     ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3: cube of Kuhn tetrahedra (config 5); 2: refined square of triangles, reflecting walls (config 2)")
     ap.add_argument("--v0", type=float, nargs=3, default=[0.0, 0.0, 0.0])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled DMMA, 3 warp-specialised DMMA, 4 / 5 Bernstein-Bezier (sparse operators, CUDA cores; 5 = face-sequential schedule), 6 Bernstein-Bezier second generation (TMA pipeline, interleaved layout)")
     ap.add_argument("--bb-tile", type=int, default=0, help="elements per CTA of the Bernstein-Bezier kernels (32, 16, 8; 0: the engine's default)")
@@ -317,9 +323,12 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     pkg = graft.load_package()
-    workload = f"cube n={args.cells} ({args.cells ** 3 * 6} tets) order {args.order} RK4"
-    config = {"workload": workload, "cells": args.cells, "order": args.order, "v0": args.v0, "boundary": "absorbing",
-              "l2": "inputs larger than L2 (state arrays of 1.6 GB each)", "partition": args.partitioner if world > 1 else "none"}
+    workload = (f"cube n={args.cells} ({args.cells ** 3 * 6} tets) order {args.order} RK4" if args.dim == 3 else
+                f"square n={args.cells} ({args.cells ** 2 * 2} triangles, reflecting walls) order {args.order} RK4")
+    npn = {3: (args.order + 1) * (args.order + 2) * (args.order + 3) // 6, 2: (args.order + 1) * (args.order + 2) // 2}[args.dim]
+    nel = args.cells ** 3 * 6 if args.dim == 3 else args.cells ** 2 * 2
+    config = {"workload": workload, "cells": args.cells, "order": args.order, "v0": args.v0, "boundary": "absorbing" if args.dim == 3 else "reflecting",
+              "l2": f"inputs larger than L2 (4 state arrays of {4 * nel * npn * 8 / 1e6:.0f} MB each, 126 MB of L2)", "partition": args.partitioner if world > 1 else "none"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -364,7 +373,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    model, cfg, mesh = build_workload(pkg, args.cells, args.order, args.v0)
+    model, cfg, mesh = build_workload(pkg, args.cells, args.order, args.v0, args.dim)
     K, Np = mesh.K, mesh.Np
     unknowns = 4 * K * Np
     if world > 1:

@@ -78,6 +78,8 @@ def load_front():
     lib.dgf_open_msh.argtypes = [C.c_char_p, C.c_int]
     lib.dgf_make_cube.restype = C.c_void_p
     lib.dgf_make_cube.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
+    lib.dgf_make_square.restype = C.c_void_p
+    lib.dgf_make_square.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
     lib.dgf_model_free.argtypes = [C.c_void_p]
     lib.dgf_warp_model.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.dgf_warp_model_local.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -178,6 +180,10 @@ class Model:
     @classmethod
     def make_cube(cls, n, lo=-10.0, hi=10.0, order=1):
         return cls(load_front().dgf_make_cube(int(n), float(lo), float(hi), int(order)))
+
+    @classmethod
+    def make_square(cls, n, lo=-10.0, hi=10.0, order=1):
+        return cls(load_front().dgf_make_square(int(n), float(lo), float(hi), int(order)))
 
     def warp(self, amp, k):
         """Curved stand-in geometry: every node moves by a smooth field (dgf_warp_model)."""

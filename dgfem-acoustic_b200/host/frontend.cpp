@@ -61,6 +61,17 @@ extern "C" dgf_model* dgf_make_cube(int n, double lo, double hi, int order) {
     }
 }
 
+extern "C" dgf_model* dgf_make_square(int n, double lo, double hi, int order) {
+    try {
+        auto* mm = new dgf_model;
+        mm->m = gml::makeSquare(n, lo, hi, order);
+        return mm;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
 extern "C" int dgf_write_msh(const dgf_model* mm, const char* path) {
     try {
         const gml::Model& m = mm->m;

@@ -795,6 +795,82 @@ Model makeCube(int n, double lo, double hi, int order, bool withBoundaryElements
     return m;
 }
 
+// Structured square [lo,hi]^2 in the z = 0 plane: n^2 cells x 2 positively oriented triangles (cells in Morton order), order p,
+// the boundary edges as line elements of the physical group "Boundary" (the 2D twin of makeCube, for the order sweep of
+// north_star config 2 on a refined square).
+Model makeSquare(int n, double lo, double hi, int order, bool withBoundaryElements) {
+    if (n < 1 || order < 1 || order > 6) throw std::runtime_error("gmshlite: makeSquare bad arguments");
+    Model m;
+    m.name = "square" + std::to_string(n);
+    const int p = order;
+    const int64_t L = (int64_t)p * n + 1;
+    if (L * L > 2000000000LL) throw std::runtime_error("gmshlite: makeSquare lattice exceeds 32-bit node tags");
+    m.maxNodeTag = (int)(L * L);
+    m.xyz.assign(3 * (size_t)(m.maxNodeTag + 1), 0.0);
+    const double h = (hi - lo) / ((double)p * n);
+    for (int64_t j = 0; j < L; ++j)
+        for (int64_t i = 0; i < L; ++i) {
+            const size_t t = 1 + (size_t)(i + L * j);
+            m.xyz[3 * t + 0] = (i == L - 1) ? hi : lo + h * i;
+            m.xyz[3 * t + 1] = (j == L - 1) ? hi : lo + h * j;
+        }
+    auto tagOf = [&](int64_t i, int64_t j) { return (int)(1 + i + L * j); };
+    m.physNames[{1, 1}] = "Boundary";
+    m.physNames[{2, 2}] = "Domain";
+    Entity surf; surf.dim = 2; surf.tag = 1; surf.phys = {2};
+    Entity curve; curve.dim = 1; curve.tag = 1; curve.phys = {1};
+    m.entities = {curve, surf};
+    static const int tri[2][3][2] = {{{0, 0}, {1, 0}, {1, 1}}, {{0, 0}, {1, 1}, {0, 1}}};
+    std::vector<std::pair<uint64_t, std::array<int, 2>>> cells;
+    cells.reserve((size_t)n * n);
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) cells.push_back({spread3(i) | spread3(j) << 1, {i, j}});
+    std::sort(cells.begin(), cells.end());
+    const RefElement& re = refElement(2, p);
+    const RefElement& rl = refElement(1, p);
+    ElemBlock tris, lines;
+    tris.entityTag = 1; tris.entityDim = 2; tris.type = re.type;
+    lines.entityTag = 1; lines.entityDim = 1; lines.type = rl.type;
+    const size_t K = cells.size() * 2;
+    tris.tags.resize(K);
+    tris.nodeTags.resize(K * re.np);
+    size_t e = 0;
+    for (auto& cell : cells) {
+        const int ci = cell.second[0], cj = cell.second[1];
+        for (int t = 0; t < 2; ++t, ++e) {
+            int64_t V[3][2];
+            for (int v = 0; v < 3; ++v) { V[v][0] = (int64_t)p * (ci + tri[t][v][0]); V[v][1] = (int64_t)p * (cj + tri[t][v][1]); }
+            for (int nn = 0; nn < re.np; ++nn) {
+                int64_t P[2] = {0, 0};
+                for (int v = 0; v < 3; ++v)
+                    for (int c = 0; c < 2; ++c) P[c] += re.bary[nn][v] * V[v][c];
+                tris.nodeTags[e * re.np + nn] = tagOf(P[0] / p, P[1] / p);
+            }
+            if (withBoundaryElements)
+                for (int lf = 0; lf < 3; ++lf) {
+                    bool onB = false;
+                    for (int c = 0; c < 2 && !onB; ++c) {
+                        const int64_t a0 = V[kTriEdges[lf][0]][c], a1 = V[kTriEdges[lf][1]][c];
+                        if (a0 == a1 && (a0 == 0 || a0 == (int64_t)p * n)) onB = true;
+                    }
+                    if (!onB) continue;
+                    const int* fn = &re.faceNodes[lf * re.nfp];
+                    for (int q = 0; q < re.nfp; ++q) lines.nodeTags.push_back(tris.nodeTags[e * re.np + fn[q]]);
+                }
+        }
+    }
+    int tag = 0;
+    if (withBoundaryElements) {
+        lines.tags.resize(lines.nodeTags.size() / rl.np);
+        for (auto& t : lines.tags) t = ++tag;
+        m.blocks.push_back(std::move(lines));
+    }
+    for (auto& t : tris.tags) t = ++tag;
+    m.maxElemTag = tag;
+    m.blocks.push_back(std::move(tris));
+    return m;
+}
+
 // =============================================================================================
 // Jacobians (Gmsh convention, straight-sided elements)
 // =============================================================================================

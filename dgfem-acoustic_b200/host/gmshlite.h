@@ -94,6 +94,7 @@ void elevate(Model& m, int order);
 // n^3 cells x 6 Kuhn tetrahedra on [lo,hi]^3, already at `order`, cells in Morton order, boundary
 // triangles in a physical group "Boundary" (tag 1). Node tags are lattice indices (no hashing).
 Model makeCube(int n, double lo, double hi, int order, bool withBoundaryElements = true);
+Model makeSquare(int n, double lo, double hi, int order, bool withBoundaryElements = true);
 
 // Jacobians as Gmsh returns them: 9 doubles per element, index u*3+x = d x_x / d u_u, with Gmsh's
 // completion for elements of dimension < 3; det as Gmsh defines it (signed for tets, a norm below).

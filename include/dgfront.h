@@ -53,6 +53,9 @@ const char* dgf_last_error(void);
 dgf_model* dgf_open_msh(const char* path, int order);
 /* synthetic cube of n^3 x 6 Kuhn tetrahedra on [lo,hi]^3 at `order` (BASELINE config 5) */
 dgf_model* dgf_make_cube(int n, double lo, double hi, int order);
+/* Structured square [lo,hi]^2: n^2 cells x 2 triangles of the given order, boundary edges in the physical group "Boundary"
+ * (the refined square of BASELINE config 2). */
+dgf_model* dgf_make_square(int n, double lo, double hi, int order);
 /* writes the model as MSH 4.0 ASCII (the format of the reference's doc meshes), e.g. to feed the reference itself */
 int dgf_write_msh(const dgf_model* m, const char* path);
 /* Curved stand-in geometry: moves EVERY node by a smooth field of amplitude amp and wave number k, which

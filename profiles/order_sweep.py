@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Order / dimension sweep (BASELINE config 2): python profiles/order_sweep.py [out.json]   (under gpurun, 1 GPU)
+Runs bench.py on tetrahedra of order 1..6 and on a refined square of triangles of order 1..6, every mesh sized so that each
+state array exceeds the 126 MB L2, with the automatic kernel choice and, where another kernel exists, that one beside it.
+One row per run: kernel, ms per stage, DOF-updates/s, fraction of the HBM roof, fraction of the FP64 roof."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+out_path = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out" / "r02_order_sweep.json"
+# (dim, order, cells, [kernel ids])   kernel 0 = automatic
+RUNS = [(3, 1, 56, [0]), (3, 2, 48, [0, 6]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0]),
+        (2, 1, 850, [0]), (2, 2, 600, [0]), (2, 3, 480, [0]), (2, 4, 400, [0]), (2, 5, 340, [0]), (2, 6, 300, [0])]
+rows = []
+for dim, order, cells, kernels in RUNS:
+    for k in kernels:
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--dim", str(dim), "--order", str(order), "--cells", str(cells), "--steps", "5", "--warmup", "3",
+               "--no-cpu-baseline", "--kernel", str(k)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        try:
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            rf = d["roofline"]
+            row = {"dim": dim, "order": order, "cells": cells, "requested_kernel": k, "kernel": d["kernel"], "workload": d["config"]["workload"],
+                   "stage_ms": rf["stage_kernel_ms"], "dof_updates_per_s": d["value"], "hbm_frac": rf["frac"], "hbm_gbs": rf["achieved"],
+                   "fp64_frac": rf["fp64"]["frac"], "fp64_tflops": rf["fp64"]["achieved"], "alg_bytes_per_launch": rf["alg_bytes_per_launch"],
+                   "alg_flops_per_launch": rf["fp64"]["alg_flops_per_launch"], "finite": d["finite"], "clocks": d["clocks"]}
+        except Exception as e:
+            row = {"dim": dim, "order": order, "cells": cells, "requested_kernel": k, "error": str(e), "stderr": r.stderr[-400:]}
+        rows.append(row)
+        print(json.dumps({k2: row.get(k2) for k2 in ("dim", "order", "kernel", "stage_ms", "dof_updates_per_s", "hbm_frac", "fp64_frac", "error")}), flush=True)
+        out_path.write_text(json.dumps({"peaks": {"hbm_gbs": "MEASURED_PEAKS.json", "fp64_tflops": 37.1}, "rows": rows}, indent=1))

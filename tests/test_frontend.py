@@ -142,6 +142,27 @@ def test_cube_generator_is_conforming(pkg):
     np.testing.assert_allclose(mesh.node_coords[a], mesh.node_coords[b], atol=1e-12)
 
 
+def test_square_generator_is_conforming(pkg, oracle_mod):
+    """The refined square of BASELINE config 2 (dgf_make_square): counts, area, matched face nodes, and the reference's loops on it
+    (oracle faithful mode) equal the collapsed operator."""
+    mesh = pkg.Mesh(pkg.Model.make_square(5, -10.0, 10.0, 3), pkg.Config())
+    assert mesh.K == 5 * 5 * 2 and mesh.desc.dim == 2 and mesh.Np == 10
+    assert int(mesh.fIsBoundary.sum()) == 4 * 5
+    assert mesh.F == (3 * mesh.K + int(mesh.fIsBoundary.sum())) // 2
+    assert abs(mesh.elJacobianDet[:, 0].sum() / 2.0 - 20.0 ** 2) < 1e-9
+    f = np.nonzero(mesh.fIsBoundary == 0)[0]
+    a = mesh.fNbrElId[f, 0][:, None] * mesh.Np + mesh.fNToElNId[f, :, 0]
+    b = mesh.fNbrElId[f, 1][:, None] * mesh.Np + mesh.fNToElNId[f, :, 1]
+    np.testing.assert_allclose(mesh.node_coords[a], mesh.node_coords[b], atol=1e-12)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(12.0, -4.0, 0.0), dt=1e-5)
+    mesh.fBC[np.nonzero(mesh.fIsBoundary)[0][::2]] = 1
+    u = np.random.default_rng(3).standard_normal((4, mesh.N))
+    orc = oracle_mod.Oracle(mesh)
+    fa, op = orc.eval_rhs(oracle_mod.Oracle.FAITHFUL, u), orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u)
+    for q in range(3):
+        assert np.linalg.norm(fa[q] - op[q]) / np.linalg.norm(op[q]) < 1e-12
+
+
 def test_msh_roundtrip_and_elevation(pkg, tmp_path):
     m1 = pkg.Model.make_cube(2, -1.0, 1.0, 1)
     m1.write_msh(tmp_path / "c.msh")

@@ -14,6 +14,8 @@ TOL = 1e-10
 def build_mesh(pkg, mesh_dir, name, order, v0=(0.0, 0.0, 0.0), c0=343.0, rho0=1.225, mixed_bc=True, cfl=0.1):
     if name.startswith("cube:"):
         model = pkg.Model.make_cube(int(name.split(":")[1]), -10.0, 10.0, order)
+    elif name.startswith("square:"):
+        model = pkg.Model.make_square(int(name.split(":")[1]), -10.0, 10.0, order)
     else:
         model = pkg.Model.open_msh(mesh_dir / name, order)
     cfg = pkg.Config()
@@ -54,6 +56,7 @@ CASES = [
     ("cube:3", 4, (30.0, 10.0, 0.0)),
     ("cube:2", 5, (1.0, 2.0, 3.0)),
     ("cube:2", 6, (0, 0, 0)),
+    ("square:7", 4, (15.0, -6.0, 0)),
 ]
 
 
