@@ -444,6 +444,8 @@ def main():
     if world > 1 and args.parity_cells > 0:
         parity = multi_gpu_parity(pkg, torch, dist, args, rank, world)
 
+    fp64_now = eng.measure_fp64_tflops() if rank == 0 else 0.0  # same box, same run (after the timed regions)
+
     if rank == 0:
         peaks, how = measured_peaks()
         v0_zero = all(v == 0.0 for v in args.v0)
@@ -468,7 +470,8 @@ def main():
                          "stage_kernel_ms": stage_ms, "alg_bytes_per_launch": bytes_stage * frac_work,
                          "fp64": {"achieved": tfl, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tfl / FP64_PEAK_TFLOPS,
                                   "alg_flops_per_launch": flops_stage * frac_work,
-                                  "peak_source": "profiles/microbench/r01_fp64_peaks_b200.txt (DMMA m8n8k4 sustained)"}},
+                                  "peak_source": "profiles/microbench/r01_fp64_peaks_b200.txt (DMMA m8n8k4 sustained)",
+                                  "peak_measured_this_run": fp64_now, "peak_measured_how": "dgb_measure_fp64_tflops: DFMA, 16 chains x 1024 threads per SM, best of 3"}},
             "clocks": clk.summary(),
         }
         if parity is not None:

@@ -367,6 +367,8 @@ def load_dgb():
     lib.dgb_synchronize.argtypes = [C.c_void_p]
     lib.dgb_last_run_ms.restype = C.c_double
     lib.dgb_last_run_ms.argtypes = [C.c_void_p]
+    lib.dgb_measure_fp64_tflops.restype = C.c_double
+    lib.dgb_measure_fp64_tflops.argtypes = [C.c_void_p]
     lib.dgb_last_stage_kernel_ms.restype = C.c_double
     lib.dgb_last_stage_kernel_ms.argtypes = [C.c_void_p]
     lib.dgb_launch_count.restype = C.c_int64
@@ -402,6 +404,9 @@ class Engine:
 
     def set_option(self, key, value):
         self._check(self.lib.dgb_set_option(self.h, key.encode(), int(value)))
+
+    def measure_fp64_tflops(self):
+        return self.lib.dgb_measure_fp64_tflops(self.h)
 
     def get_option(self, key):
         v = C.c_int(0)

@@ -160,9 +160,9 @@ struct dgb_handle {
     double *dProbeWBB = nullptr, *dRecvWBB = nullptr;
     std::vector<int32_t> srcElOff;   // per source: its range in dSrcElList
     int32_t *dSrcElList = nullptr, *dSrcNodeOff = nullptr, *dSrcNodeLocal = nullptr;
-    // Measured on B200 (profiles/r02/): the second-generation Bernstein kernel beats the dense DMMA kernels on tetrahedra of
-    // order >= 3, with and without mean flow
-    StageKernel autoKernel() const { return (bb2Kernel.launch && M.order >= 3 && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
+    // Measured on B200 (profiles/r02_order_sweep.json): the second-generation Bernstein kernel beats the CUDA-core kernel on
+    // tetrahedra from order 2 on and the dense DMMA kernels at orders 3 / 4, with and without mean flow
+    StageKernel autoKernel() const { return (bb2Kernel.launch && M.order >= 2 && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
     bool preferBB2 = true;
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
@@ -1649,6 +1649,13 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
         else if (k == "time_stages") h->timeStages = value ? 1 : 0;
         else throw DgbException(DGB_ERR_ARG, "unknown option " + k);
     });
+}
+
+double dgb_measure_fp64_tflops(dgb_handle* h) {
+    if (!h) return 0.0;
+    DeviceScope onDevice(h);
+    cudaStreamSynchronize(h->stream);
+    return measureFp64Tflops(h->stream);
 }
 
 int dgb_get_option(dgb_handle* h, const char* key, int* value) {

@@ -125,6 +125,8 @@ void launchUnpackElements(double* y, int64_t stride, int Np, int firstElem, int 
 void launchGatherState(const double* globalHost, int64_t Ng, const int32_t* l2g, int K, int Np, double* local, int64_t stride, cudaStream_t s);
 void launchScatterState(double* globalHost, int64_t Ng, const int32_t* l2g, int K, int Np, const double* local, int64_t stride, cudaStream_t s);
 
+double measureFp64Tflops(cudaStream_t s);  // instrumentation: DFMA issue peak of the current device (state_io.cu)
+
 // direct peer-to-peer halo exchange (halo_p2p.cu); tables are passed by value as kernel arguments
 struct PeerTargets { double* arr[MAX_PEERS]; long long stride[MAX_PEERS]; };   // the peers' copy of the produced array, [4][stride]
 struct PeerFlags { unsigned long long* flag[MAX_PEERS]; int n; };              // THIS rank's slot in each peer's flag array

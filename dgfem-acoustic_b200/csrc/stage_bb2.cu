@@ -41,7 +41,15 @@ constexpr int kTE2 = 8;  // elements per tile: 8 elements x 4 fields = the 32 la
 template <int P>
 struct BB2Cfg {
     static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
-    static constexpr int TILE = kTE2 * NP * 4;         // doubles of one state tile
+    // Element stride of a state tile in shared memory (doubles). Lane (element, field) reads coefficient i of its element at
+    // el*ES + i*4 + field: the four elements of a half-warp must start 4 (mod 8) doubles apart to hit disjoint 8-word bank windows. Np*4 does
+    // at order 4 (140) — the tile is then one contiguous run, ONE bulk copy — but not at orders 3 and 5 (80 and 224 doubles: every
+    // element on the same banks, measured 4-way conflicts) or 2 (40: 2-way): those tiles are padded and travel as one bulk copy
+    // per element, issued by lanes 0..7.
+    static constexpr int padFor(int n) { int pad = 0; while ((n + pad) % 8 != 4) pad += 4; return pad; }
+    static constexpr int PAD = padFor(NP * 4);
+    static constexpr int ES = NP * 4 + PAD;
+    static constexpr int TILE = kTE2 * ES;             // doubles of one state tile in shared memory
     static constexpr int TRS = NFP * 4;                // element stride of the trace buffer: the 64-bit reads of lane (element, field) are conflict free
     static constexpr int GI = (2 * NFP + 31) / 32;     // gather instructions per (element, face): 2 x 16 B per trace
     static constexpr int FCS = 10;                     // doubles per (local face, element): app, aps, b, c, d, n (+2: conflict-free 128-bit reads)
@@ -126,10 +134,14 @@ __device__ __forceinline__ void fieldVolumeInterleaved(int q, const double* col,
     bb::elevateAdd<N>(t, -1.0, out);
 }
 
+// resident warps per SM the register allocation aims at (the shared memory of a warp allows about as many)
+__host__ __device__ constexpr int bb2WarpsPerSm(int p) { return p <= 2 ? 16 : p == 3 ? 12 : p == 4 ? 8 : 6; }
+
 template <int P>
-__global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
+__global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
     using C = BB2Cfg<P>;
-    constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS;
+    constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES;
+    constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
     extern __shared__ __align__(128) unsigned char smemRaw2[];
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
@@ -199,11 +211,24 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         for (int j = 0; j < 9; ++j) G[j] = M.Ginv[(int64_t)e * 9 + j];
     };
     auto tileBytes = [&](int tt) { return (uint32_t)(min(kTE2, A.eEnd - (A.eBegin + tt * kTE2)) * NP * 32); };
-    auto issueY = [&](int tt) {  // lane 0 only
-        const uint32_t bytes = tileBytes(tt);
-        mbarExpectTx(&bars[0], bytes);
-        bulkLoad(sY, A.yin + (int64_t)(A.eBegin + tt * kTE2) * NP * 4, bytes, &bars[0]);
+    // Tile copies (warp-collective). Contiguous tiles: lane 0 moves the whole tile; padded tiles: lane l moves element l.
+    auto loadTile = [&](double* dst, const double* src, uint32_t bytes, unsigned long long* bar) {
+        if (lane == 0) mbarExpectTx(bar, bytes);
+        if constexpr (kPerElement) {
+            __syncwarp();
+            if (lane * (NP * 32) < (int)bytes) bulkLoad(dst + lane * ES, src + lane * (NP * 4), NP * 32, bar);
+        } else {
+            if (lane == 0) bulkLoad(dst, src, bytes, bar);
+        }
     };
+    auto storeTile = [&](double* dst, const double* src, uint32_t bytes) {  // the caller commits
+        if constexpr (kPerElement) {
+            if (lane * (NP * 32) < (int)bytes) bulkStore(dst + lane * (NP * 4), src + lane * ES, NP * 32);
+        } else {
+            if (lane == 0) bulkStore(dst, src, bytes);
+        }
+    };
+    auto issueY = [&](int tt) { loadTile(sY, A.yin + (int64_t)(A.eBegin + tt * kTE2) * NP * 4, tileBytes(tt), &bars[0]); };
     // traces of canonical face J for the tile whose (flags, neighbour) pairs lie in meta: one neighbour element per
     // instruction (<= 9 cache lines), two 16-byte halves per trace; boundary faces and idle lanes copy zeros
     auto issueTraces = [&](int J, const int2* meta) {
@@ -229,7 +254,7 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
     int flags, nbr;
     double fg[4], G[9];
     loadMeta(t, flags, nbr, fg, G);
-    if (lane == 0) issueY(t);
+    issueY(t);
     sMeta[lane] = make_int2(flags, nbr);
     __syncwarp();
     if (!haloReady && touchesBorder(t)) waitPeers();
@@ -269,19 +294,15 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         int flagsN = 0, nbrN = -1;
         double fgN[4] = {0, 0, 0, 0}, GN[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (more) loadMeta(tn, flagsN, nbrN, fgN, GN);
-        if (lane == 0) {
-            if (loadA) {  // needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
-                mbarExpectTx(&bars[2], bytes);
-                bulkLoad(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
-            }
-            if (more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
-        }
+        // acc is needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
+        if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
+        if (lane == 0 && more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
         mbarWait2(&bars[0], phY);
         phY ^= 1;
         __syncwarp();
 
         double out[NP];
-        fieldVolumeInterleaved<P>(q, sY + el * NP * 4, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
+        fieldVolumeInterleaved<P>(q, sY + el * ES, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
 
 #pragma unroll 1
         for (int J = 0; J < 4; ++J) {
@@ -303,7 +324,7 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
             cpWaitAll();
             __syncwarp();
             double x[NFP];
-            const double* const own = sY + el * NP * 4 + q;
+            const double* const own = sY + el * ES + q;
             const double* const tr = sT + el * TRS + q;
 #pragma unroll
             for (int b = 0; b < NFP; ++b) {
@@ -318,10 +339,7 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
             if (J < 3) issueTraces(J + 1, meta);
             else {
                 // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
-                if (lane == 0 && loadU) {
-                    mbarExpectTx(&bars[1], bytes);
-                    bulkLoad(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
-                }
+                if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
                 if (more) {
                     metaN[lane] = make_int2(flagsN, nbrN);
                     __syncwarp();
@@ -343,8 +361,8 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
         if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
         {
-            double* const pu = sY + el * NP * 4 + q;
-            double* const pa = sA + el * NP * 4 + q;
+            double* const pu = sY + el * ES + q;
+            double* const pa = sA + el * ES + q;
             const double dt = A.dt;
             switch (mode) {
                 case MODE_RK1:
@@ -375,11 +393,9 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
         }
         fenceProxyAsync();
         __syncwarp();
-        if (lane == 0) {
-            bulkStore(uDst + (int64_t)e0 * NP * 4, sY, bytes);
-            if (storeA) bulkStore(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
-            bulkCommit();
-        }
+        storeTile(uDst + (int64_t)e0 * NP * 4, sY, bytes);
+        if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
+        bulkCommit();
         if (fx != nullptr && touchesBorder(t)) {
             // lane l ships element l of the tile to every peer that holds it as a halo element: one bulk store per target,
             // straight from the shared-memory tile over NVLink
@@ -387,14 +403,13 @@ __global__ void __launch_bounds__(32) stageBB2Kernel(DeviceMesh M, StageArgs A, 
             if (lane < (int)(bytes / (NP * 32)) && k >= 0) {
                 const int p1 = fx->pushOff[k + 1];
                 for (int p = fx->pushOff[k]; p < p1; ++p)
-                    bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sY + lane * NP * 4, NP * 32);
+                    bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sY + lane * ES, NP * 32);
                 bulkCommit();
             }
-            bulkWaitRead();
-            __syncwarp();
         }
-        if (lane == 0 && more) {
-            bulkWaitRead();  // both tiles have been read by the stores
+        if (more) {
+            bulkWaitRead();  // both tiles have been read by the stores (every lane waits for the copies it issued)
+            __syncwarp();
             issueY(tn);
         }
         if (!more) break;

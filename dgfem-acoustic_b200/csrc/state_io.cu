@@ -50,3 +50,52 @@ void launchScatterState(double* globalHost, int64_t Ng, const int32_t* l2g, int 
 }
 
 }  // namespace dgb
+
+// ---- instrumentation: FP64 issue peak of the current device, measured on the spot (dgb_measure_fp64_tflops) -------------------
+// 16 independent DFMA chains per thread, 512 threads per CTA, 2 CTAs per SM: the configuration that reaches the plateau in
+// profiles/microbench/r01_fp64_peaks_b200.txt (36.8 TFLOP/s DFMA; the DMMA pipe is the same pipe, 37.1).
+namespace dgb {
+namespace {
+__global__ void __launch_bounds__(512) dfmaPeakKernel(double* out, int iters) {
+    double a[16];
+    const double x = 1.0000001 + threadIdx.x * 1e-9, y = 0.999999;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = i * 0.1 + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+double measureFp64Tflops(cudaStream_t s) {
+    int dev = 0, numSm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev);
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = 2 * numSm, iters = 20000;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // the first repetition warms up
+        cudaEventRecord(e0, s);
+        dfmaPeakKernel<<<grid, 512, 0, s>>>(out, iters);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 16 * iters * 512.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : 0.0;
+}
+}  // namespace dgb

@@ -152,8 +152,11 @@ int dgb_synchronize(dgb_handle* h);
 double dgb_last_run_ms(dgb_handle* h);        /* CUDA-event time of the last dgb_run */
 double dgb_last_stage_kernel_ms(dgb_handle* h); /* mean CUDA-event duration of the stage kernel in the last run */
 int64_t dgb_launch_count(dgb_handle* h);      /* kernels launched by this handle so far */
+/* FP64 (DFMA) issue peak of the handle's device in TFLOP/s, measured on the spot (~10 ms): the denominator of the FP64
+ * roofline fraction bench.py reports, from the same box in the same run. */
+double dgb_measure_fp64_tflops(dgb_handle* h);
 /* Options (all integers):
- *   "kernel"   0 automatic (default: the second-generation Bernstein-Bezier kernel for tetrahedra of order >= 3, else the
+ *   "kernel"   0 automatic (default: the second-generation Bernstein-Bezier kernel for tetrahedra of order 2..5, else the
  *              CUDA-core kernel), 1 generic CUDA cores, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow),
  *              4 / 5 first-generation Bernstein-Bezier kernels (tetrahedra of order 2..5; 5 = face-sequential schedule;
  *              "bb_tile": 32 / 16 / 8 elements per CTA), 6 second-generation Bernstein-Bezier kernel (csrc/stage_bb2.cu).
