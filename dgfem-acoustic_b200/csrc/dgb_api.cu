@@ -586,8 +586,17 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                             }
                     h->bbPermOffset = (size_t)4 * Nfp + (size_t)M.nMaps * 4 * Nfp;
                     std::copy(h->permG2C.begin(), h->permG2C.end(), tab.begin() + h->bbPermOffset);
+                    // the neighbour table once more with padded, 16-byte aligned rows (the trace gathers of stage_bb2 load a row with 128-bit loads)
+                    const size_t RS = (size_t)(Nfp + 15) / 16 * 16;
+                    const size_t nbr16Offset = (tab.size() + 15) / 16 * 16;
+                    tab.resize(nbr16Offset + (size_t)M.nMaps * 4 * RS, 0);
+                    for (int mp = 0; mp < M.nMaps; ++mp)
+                        for (int J = 0; J < 4; ++J)
+                            for (int b = 0; b < Nfp; ++b)
+                                tab[nbr16Offset + ((size_t)mp * 4 + J) * RS + b] = tab[(size_t)4 * Nfp + ((size_t)mp * 4 + J) * Nfp + b];
                     h->dBBTab = devUpload(tab);
                     M.bbTab = h->dBBTab;
+                    M.bbNbr16 = h->dBBTab + nbr16Offset;  // cudaMalloc returns 256-byte aligned memory
                     for (int J = 0; J < 4; ++J) M.bbFaceLf[J] = S.T.faceLf[J];
                     std::vector<double> VC((size_t)Np * Np), VinvC((size_t)Np * Np);
                     for (int n = 0; n < Np; ++n)

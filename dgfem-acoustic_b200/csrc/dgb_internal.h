@@ -49,6 +49,7 @@ struct DeviceMesh {
     // 2D index b, then [nMaps][4][Nfp] the neighbour's coefficient for (face-pairing map, face J, b) — and the mesh's
     // local face of canonical face J
     const uint8_t* bbTab;
+    const uint8_t* bbNbr16;  // [nMaps][4][RS] the second table again with rows padded to RS = 16*ceil(Nfp/16) bytes, 16-byte aligned (one or two 128-bit loads per row)
     uint8_t bbFaceLf[4];
     uint8_t bbOwn[4][28];  // the first table again, in the kernel's parameter space (uniform run-time index)
 };

@@ -19,14 +19,15 @@
 //         (cp.async.bulk, mbarrier complete_tx) — no LSU instruction, no register, no L1 wavefront;
 //       - the results leave by TMA bulk stores straight from the shared-memory tiles they were combined in;
 //       - the neighbour traces of ONE face at a time are gathered with 16-byte cp.async (zero-filled on boundary faces),
-//         one neighbour element per instruction (<= 9 cache lines), issued one lift ahead of their use;
+//         lane (element, slot) fetching its own element's trace (the per-element address work is done once per face),
+//         issued one lift ahead of their use;
 //       - the next tile's stage input is requested as soon as the last face has read the current one, its face metadata
 //         and inverse Jacobian travel in registers one tile ahead.
 //   * 6 warps per SM at order 4 (33 KB of shared memory each): the latency that occupancy hid badly is hidden by the
 //     copies in flight instead.
 //
-// Shared memory of a warp: stage-input tile | acc tile | u tile (3 x 8*Np*32 B) | one face's traces / lift inputs | face
-// coefficients | 2 mbarriers | own-trace index table.
+// Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded at orders 2 / 3 / 5) | one face's traces |
+// face coefficients | 3 mbarriers.
 #include "bb_ops.h"
 #include "dgb_device.cuh"
 #include "dgb_internal.h"
@@ -51,10 +52,10 @@ struct BB2Cfg {
     static constexpr int ES = NP * 4 + PAD;
     static constexpr int TILE = kTE2 * ES;             // doubles of one state tile in shared memory
     static constexpr int TRS = NFP * 4;                // element stride of the trace buffer: the 64-bit reads of lane (element, field) are conflict free
-    static constexpr int GI = (2 * NFP + 31) / 32;     // gather instructions per (element, face): 2 x 16 B per trace
+    static constexpr int NIT = (NFP + 1) / 2;          // gather instructions per face: lane (element, slot) moves the 16-byte chunk 4*it + slot of its element's trace
+    static constexpr int RS = (NFP + 15) / 16 * 16;    // row stride (bytes) of DeviceMesh::bbNbr16
     static constexpr int FCS = 10;                     // doubles per (local face, element): app, aps, b, c, d, n (+2: conflict-free 128-bit reads)
-    static constexpr size_t SMEM = (size_t)(2 * TILE + kTE2 * TRS + 32 * FCS + 4 /* dummy gather target */) * sizeof(double) + 4 * sizeof(unsigned long long) +
-                                   2 * 32 * sizeof(int2);
+    static constexpr size_t SMEM = (size_t)(2 * TILE + kTE2 * TRS + 32 * FCS) * sizeof(double) + 4 * sizeof(unsigned long long);
     static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
 };
 
@@ -147,9 +148,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
     double* const sT = sA + C::TILE;                         // [8][TRS]  traces of the current face
     double* const sFc = sT + kTE2 * TRS;                     // [4][8][FCS] face coefficients of the tile
-    double* const sDummy = sFc + 32 * C::FCS;                // target of the idle gather lanes
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sDummy + 4);  // [0] stage input, [1] u, [2] acc
-    int2* const sMeta = reinterpret_cast<int2*>(bars + 4);   // [2][32] (flags, neighbour) per (element, local face): this tile / the next one
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sFc + 32 * C::FCS);  // [0] stage input, [1] u, [2] acc
 
     const int lane = threadIdx.x, el = lane >> 2, q = lane & 3;
     const unsigned FULL = 0xffffffffu;
@@ -229,24 +228,32 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
         }
     };
     auto issueY = [&](int tt) { loadTile(sY, A.yin + (int64_t)(A.eBegin + tt * kTE2) * NP * 4, tileBytes(tt), &bars[0]); };
-    // traces of canonical face J for the tile whose (flags, neighbour) pairs lie in meta: one neighbour element per
-    // instruction (<= 9 cache lines), two 16-byte halves per trace; boundary faces and idle lanes copy zeros
-    auto issueTraces = [&](int J, const int2* meta) {
-        const int lf = M.bbFaceLf[J];
-        const unsigned char* tab = M.bbTab + 4 * NFP + J * NFP;
+    // Traces of canonical face J for the tile whose face metadata (lane = (element, local face)) are flagsT / nbrT. Lane
+    // (element, slot) moves the 16-byte chunks 4*it + slot of ITS element's trace: chunk j is half j&1 of the 32-byte record
+    // (4 fields) of trace coefficient j>>1. Everything that depends on the element — neighbour, pairing map, base address — is
+    // formed once per face; an iteration is one byte extraction, one 64-bit multiply-add and the copy. Boundary faces copy zeros.
+    auto issueTraces = [&](int J, int flagsT, int nbrT) {
+        const int srcLane = (lane & ~3) | M.bbFaceLf[J];
+        const int fl = __shfl_sync(FULL, flagsT, srcLane), nb = __shfl_sync(FULL, nbrT, srcLane);
+        const bool interior = (fl & FLAG_BC_MASK) == FACE_INTERIOR && nb >= 0;
+        uint32_t w[C::RS / 4];
+        {
+            const uint4* row = reinterpret_cast<const uint4*>(M.bbNbr16 + (size_t)((interior ? (fl >> FLAG_MAP_SHIFT) : 0) * 4 + J) * C::RS);
 #pragma unroll
-        for (int r = 0; r < kTE2; ++r) {
-            const int2 m = meta[r * 4 + lf];
-            const bool interior = (m.x & FLAG_BC_MASK) == FACE_INTERIOR && m.y >= 0;
-            const unsigned char* mp = tab + (m.x >> FLAG_MAP_SHIFT) * (4 * NFP);
-            const double* base = A.yin + (int64_t)(interior ? m.y : 0) * (NP * 4);
-#pragma unroll
-            for (int g = 0; g < C::GI; ++g) {
-                const int h = lane + 32 * g, b = h >> 1, half = h & 1;
-                const bool act = b < NFP;
-                const int ci = (act && interior) ? mp[b] : 0;
-                cpAsync16(act ? sT + r * TRS + b * 4 + half * 2 : sDummy + half * 2, base + ci * 4 + half * 2, (act && interior) ? 16u : 0u);
+            for (int k = 0; k < C::RS / 16; ++k) {
+                const uint4 v = row[k];
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
             }
+        }
+        const int hb = (lane >> 1) & 1;
+        const uint32_t selLo = 0x4440u | hb, selHi = 0x4440u | (2 + hb);  // byte 2*it + hb of the row, zero-extended
+        const double* const base = A.yin + (int64_t)(interior ? nb : 0) * (NP * 4) + (lane & 1) * 2;
+        double* const dst = sT + el * TRS + (lane & 3) * 2;
+        const uint32_t sz = interior ? 16u : 0u;
+#pragma unroll
+        for (int it = 0; it < C::NIT; ++it) {
+            const uint32_t ci = __byte_perm(w[it >> 1], 0u, (it & 1) ? selHi : selLo);
+            if (2 * it + 1 < NFP || hb == 0) cpAsync16(dst + it * 8, base + ci * 4, sz);
         }
         cpCommit();
     };
@@ -255,20 +262,15 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
     double fg[4], G[9];
     loadMeta(t, flags, nbr, fg, G);
     issueY(t);
-    sMeta[lane] = make_int2(flags, nbr);
-    __syncwarp();
     if (!haloReady && touchesBorder(t)) waitPeers();
-    issueTraces(0, sMeta);
+    issueTraces(0, flags, nbr);
     uint32_t phY = 0, phU = 0, phA = 0;
-    int mb = 0;  // which half of sMeta holds this tile
 
     for (;;) {
         const int tn = t + (int)gridDim.x;
         const bool more = tn < nTiles;
         const int e0 = A.eBegin + t * kTE2;
         const uint32_t bytes = tileBytes(t);
-        const int2* const meta = sMeta + 32 * mb;
-        int2* const metaN = sMeta + 32 * (mb ^ 1);
 
         // face coefficients of the tile (lane = (element, local face)), barycentric gradients of the lane's element
         {
@@ -336,15 +338,13 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
                 x[b] = A1 * a + (A2 * ap + A3 * S);
             }
             __syncwarp();  // the trace buffer is free: the next face's traces travel while this face is lifted
-            if (J < 3) issueTraces(J + 1, meta);
+            if (J < 3) issueTraces(J + 1, flags, nbr);
             else {
                 // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
                 if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
                 if (more) {
-                    metaN[lane] = make_int2(flagsN, nbrN);
-                    __syncwarp();
                     if (!haloReady && touchesBorder(tn)) waitPeers();
-                    issueTraces(0, metaN);
+                    issueTraces(0, flagsN, nbrN);
                 }
             }
             double zl[NP];
@@ -414,7 +414,6 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
         }
         if (!more) break;
         t = tn;
-        mb ^= 1;
         flags = flagsN;
         nbr = nbrN;
 #pragma unroll
