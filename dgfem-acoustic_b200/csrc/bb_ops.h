@@ -195,6 +195,153 @@ BB_HD void liftFace(const double (&x)[tri(N)], double (&out)[tet(N)]) {
     scatterAddFace<N, J>(zl, out);
 }
 
+// ---- triangles ----------------------------------------------------------------------------------------------------------
+// The same operators one dimension down (configs 1 and 2 are 2D). Volume indices a = (a0,a1,a2), |a| = N, in the
+// canonical order fidx(N, a1, a2); an edge carries the N+1 coefficients with a_J = 0 (J = the vertex opposite the edge),
+// indexed by b1 where (b0, b1) are the other two entries in increasing vertex order. The lift has the very same closed form
+// with the 1D elevation (E_M x)_g = g0 x_{g-e0} + g1 x_{g-e1}:  y = E_N^T E_N x,  z_l = -1/(l+1) E_{N-l}^T z_{l-1}
+// (checked against Mref^-1 E_lf Mf at create time and in tests/test_bb_ops.py, N = 1..6).
+namespace d2 {
+
+template <int N, int J>
+BB_HD constexpr int layerIdx(int l, int b1) {
+    const int b0 = N - l - b1;
+    const int a1 = J == 0 ? b0 : J == 1 ? l : b1;
+    const int a2 = J == 0 ? b1 : J == 1 ? b1 : l;
+    return fidx(N, a1, a2);
+}
+
+template <int N, bool ACCUMULATE>
+BB_HD void dirDeriv(const double (&c)[tri(N)], const double (&w)[3], double (&t)[tri(N - 1)]) {
+    BB_UNROLL
+    for (int b1 = 0; b1 <= N - 1; ++b1) {
+        BB_UNROLL
+        for (int b2 = 0; b2 <= N - 1 - b1; ++b2) {
+            double s = w[0] * c[fidx(N, b1, b2)];
+            s = s + w[1] * c[fidx(N, b1 + 1, b2)];
+            s = s + w[2] * c[fidx(N, b1, b2 + 1)];
+            const int i = fidx(N - 1, b1, b2);
+            t[i] = ACCUMULATE ? t[i] + s : s;
+        }
+    }
+}
+
+template <int N>
+BB_HD void elevateAdd(const double (&t)[tri(N - 1)], double scale, double (&out)[tri(N)]) {
+    BB_UNROLL
+    for (int a1 = 0; a1 <= N; ++a1) {
+        BB_UNROLL
+        for (int a2 = 0; a2 <= N - a1; ++a2) {
+            const int a0 = N - a1 - a2;
+            double s = 0.0;
+            if (a0 > 0) s = s + a0 * t[fidx(N - 1, a1, a2)];
+            if (a1 > 0) s = s + a1 * t[fidx(N - 1, a1 - 1, a2)];
+            if (a2 > 0) s = s + a2 * t[fidx(N - 1, a1, a2 - 1)];
+            const int i = fidx(N, a1, a2);
+            out[i] = out[i] + scale * s;
+        }
+    }
+}
+
+// (E_M^T w)_b = (b0 + 1) w_b + (b1 + 1) w_{b+e1} : degree M+1 -> M on an edge (index = b1)
+template <int M>
+BB_HD void edgeLower(const double (&w)[M + 2], double (&z)[M + 1]) {
+    BB_UNROLL
+    for (int b1 = 0; b1 <= M; ++b1) z[b1] = (M - b1 + 1) * w[b1] + (b1 + 1) * w[b1 + 1];
+}
+
+// (E_M x)_g = g0 x_g + g1 x_{g-e1} : degree M -> M+1 on an edge
+template <int M>
+BB_HD void edgeRaise(const double (&x)[M + 1], double (&w)[M + 2]) {
+    BB_UNROLL
+    for (int g1 = 0; g1 <= M + 1; ++g1) {
+        const int g0 = M + 1 - g1;
+        double s = 0.0;
+        if (g0 > 0) s = s + g0 * x[g1];
+        if (g1 > 0) s = s + g1 * x[g1 - 1];
+        w[g1] = s;
+    }
+}
+
+BB_HD constexpr int layerOff(int N, int l) {
+    int s = 0;
+    for (int k = 0; k < l; ++k) s += N - k + 1;
+    return s;
+}
+
+template <int N, int L>
+struct LiftLayers {
+    static BB_HD void run(const double (&z)[N - L + 1], double (&zl)[tri(N)]) {
+        BB_UNROLL
+        for (int b = 0; b <= N - L; ++b) zl[layerOff(N, L) + b] = z[b];
+        if constexpr (L < N) {
+            double zn[N - L];
+            edgeLower<N - L - 1>(z, zn);
+            LiftLayers<N, L + 1>::run(zn, zl);
+        }
+    }
+};
+
+// all layers of LIFT x in edge-local order, layer l still to be multiplied by layerScale(l)
+template <int N>
+BB_HD void liftFaceLocal(const double (&x)[N + 1], double (&zl)[tri(N)]) {
+    double w[N + 2], y[N + 1];
+    edgeRaise<N>(x, w);
+    edgeLower<N>(w, y);
+    LiftLayers<N, 0>::run(y, zl);
+}
+
+template <int N, int J>
+BB_HD void scatterAddFace(const double (&zl)[tri(N)], double (&out)[tri(N)]) {
+    BB_UNROLL
+    for (int l = 0; l <= N; ++l) {
+        BB_UNROLL
+        for (int b1 = 0; b1 <= N - l; ++b1) {
+            const int i = layerIdx<N, J>(l, b1);
+            const double v = zl[layerOff(N, l) + b1];
+            out[i] = l == 0 ? out[i] + v : out[i] + layerScale(l) * v;
+        }
+    }
+}
+
+template <int N, int J>
+BB_HD void liftFace(const double (&x)[N + 1], double (&out)[tri(N)]) {
+    double zl[tri(N)];
+    liftFaceLocal<N>(x, zl);
+    scatterAddFace<N, J>(zl, out);
+}
+
+}  // namespace d2
+
+// One interface over both simplices for the kernels that are written once (stage_bb2.cu): NV vertices / faces, NP volume and
+// NFP face coefficients, ND coefficients of degree N-1. LIFT x = FACE_SCALE * scatter(liftLocal(x)): the closed forms are those
+// of a reference face of measure 1/2 (triangle) resp. 1 (edge), Gmsh's reference edge [-1, 1] has measure 2 — the callers fold
+// the factor into Fscale.
+template <int DIM, int N>
+struct Simplex;
+template <int N>
+struct Simplex<3, N> {
+    static constexpr int NV = 4, NP = tet(N), NFP = tri(N), ND = tet(N - 1);
+    static constexpr double FACE_SCALE = 1.0;
+    static BB_HD void dirDerivAcc(const double (&c)[NP], const double (&w)[NV], double (&t)[ND]) { dirDeriv<N, true>(c, w, t); }
+    static BB_HD void elevate(const double (&t)[ND], double scale, double (&out)[NP]) { elevateAdd<N>(t, scale, out); }
+    static BB_HD void liftLocal(const double (&x)[NFP], double (&zl)[NP]) { liftFaceLocal<N>(x, zl); }
+    template <int J>
+    static BB_HD void scatterAdd(const double (&zl)[NP], double (&out)[NP]) { scatterAddFace<N, J>(zl, out); }
+};
+template <int N>
+struct Simplex<2, N> {
+    static constexpr int NV = 3, NP = tri(N), NFP = N + 1, ND = tri(N - 1);
+    static constexpr double FACE_SCALE = 2.0;
+    static BB_HD void dirDerivAcc(const double (&c)[NP], const double (&w)[NV], double (&t)[ND]) { d2::dirDeriv<N, true>(c, w, t); }
+    static BB_HD void elevate(const double (&t)[ND], double scale, double (&out)[NP]) { d2::elevateAdd<N>(t, scale, out); }
+    static BB_HD void liftLocal(const double (&x)[NFP], double (&zl)[NP]) { d2::liftFaceLocal<N>(x, zl); }
+    template <int J>
+    static BB_HD void scatterAdd(const double (&zl)[NP], double (&out)[NP]) {
+        if constexpr (J < 3) d2::scatterAddFace<N, J>(zl, out);
+    }
+};
+
 constexpr int MAX_ORDER = 6, MAX_NP = tet(MAX_ORDER), MAX_NFP = tri(MAX_ORDER);
 
 // ---- face inputs of the lift ---------------------------------------------------------------------------------------------

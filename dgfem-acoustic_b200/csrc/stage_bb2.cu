@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
         // acc is needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
         if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
         if (lane == 0 && more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
+        // u can only be requested when the last face has read the stage-input tile it replaces (one lift before it is needed):
+        // bring it to L2 now, so that the request finds it there
+        if (lane == 0 && loadU && mode != MODE_RK1) bulkPrefetchL2(uSrc + (int64_t)e0 * NP * 4, bytes);
         mbarWait2(&bars[0], phY);
         phY ^= 1;
         __syncwarp();
