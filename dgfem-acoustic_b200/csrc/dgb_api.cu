@@ -162,7 +162,9 @@ struct dgb_handle {
     int32_t *dSrcElList = nullptr, *dSrcNodeOff = nullptr, *dSrcNodeLocal = nullptr;
     // Measured on B200 (profiles/r02_order_sweep.json): the second-generation Bernstein kernel beats the CUDA-core kernel on
     // tetrahedra from order 2 on and the dense DMMA kernels at orders 3 / 4, with and without mean flow
-    StageKernel autoKernel() const { return (bb2Kernel.launch && M.order >= 2 && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
+    // measured (profiles/r02_order_sweep.json): the second-generation Bernstein kernel wins on triangles of every order and on tetrahedra
+    // of order >= 2; tetrahedra of order 1 keep the generic kernel
+    StageKernel autoKernel() const { return (bb2Kernel.launch && (M.order >= 2 || M.dim == 2) && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
     bool preferBB2 = true;
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
@@ -545,45 +547,47 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         }
         // Bernstein-Bezier path (opt-in): conversion matrices, permutation tables, self-check of the closed-form lift
         h->bbKernel = curved ? StageKernel{} : selectBBKernel(dim, d->order);
+        const StageKernel bb2Candidate = curved ? StageKernel{} : selectBB2Kernel(dim, d->order);
         if (curved) h->bbWhyNot = "curved elements";
-        else if (!h->bbKernel.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra, orders 2..5)";
+        else if (!h->bbKernel.launch && !bb2Candidate.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra of orders 1..5, triangles of orders 1..6)";
         else {
             try {
                 const bb::Setup S = bb::buildSetup(d);
                 double dev = 1.0;
                 switch (d->order) {
+                    case 1: dev = bb::liftDeviation<1>(S); break;
                     case 2: dev = bb::liftDeviation<2>(S); break;
                     case 3: dev = bb::liftDeviation<3>(S); break;
                     case 4: dev = bb::liftDeviation<4>(S); break;
                     case 5: dev = bb::liftDeviation<5>(S); break;
+                    case 6: dev = bb::liftDeviation<6>(S); break;
                     default: break;
                 }
                 if (!(dev < 1e-11)) throw std::runtime_error("closed-form lift deviates from the dense one by " + std::to_string(dev));
                 for (int lf = 0; lf < Nf; ++lf)
                     for (int m = 0; m < Nfp; ++m)
                         if (S.faceNodes[(size_t)lf * Nfp + m] != H.faceNodes[(size_t)lf * Nfp + m]) throw std::runtime_error("face-node tables disagree");
-                setBBTables(d->order, S.T);
-                CUDA_CHECK(cudaGetLastError());
                 h->hostV = S.V;
                 h->dV = devUpload(S.V);
                 h->dVinv = devUpload(S.Vinv);
-                h->bbSeqKernel = selectBBKernel(dim, d->order, 1);
+                if (h->bbKernel.launch) {  // first generation (tetrahedra): permutation tables in constant memory
+                    setBBTables(d->order, S.T);
+                    CUDA_CHECK(cudaGetLastError());
+                    h->bbSeqKernel = selectBBKernel(dim, d->order, 1);
+                }
                 // second generation: canonical coefficient order, interleaved fields
-                h->bb2Kernel = selectBB2Kernel(dim, d->order);
+                h->bb2Kernel = bb2Candidate;
                 {
-                    const int N = d->order;
                     h->permG2C.assign(Np, 0);
                     for (int i = 0; i < Np; ++i) h->permG2C[S.T.permC2G[i]] = (uint8_t)i;
                     std::vector<uint8_t> tab((size_t)4 * Nfp + (size_t)M.nMaps * 4 * Nfp + Np, 0);
-                    for (int J = 0; J < 4; ++J)
-                        for (int b1 = 0; b1 <= N; ++b1)
-                            for (int b2 = 0; b2 <= N - b1; ++b2) {
-                                const int b = bb::fidx(N, b1, b2);
-                                tab[(size_t)J * Nfp + b] = (uint8_t)bb::layerIdxRt(N, J, 0, b1, b2);
-                                M.bbOwn[J][b] = tab[(size_t)J * Nfp + b];
-                                for (int mp = 0; mp < M.nMaps; ++mp)
-                                    tab[(size_t)4 * Nfp + ((size_t)mp * 4 + J) * Nfp + b] = h->permG2C[maps[(size_t)mp * Nfp + S.T.facePos[J][b]]];
-                            }
+                    for (int J = 0; J < Nf; ++J)
+                        for (int b = 0; b < Nfp; ++b) {
+                            tab[(size_t)J * Nfp + b] = (uint8_t)S.ownIdx[(size_t)J * Nfp + b];
+                            M.bbOwn[J][b] = tab[(size_t)J * Nfp + b];
+                            for (int mp = 0; mp < M.nMaps; ++mp)
+                                tab[(size_t)4 * Nfp + ((size_t)mp * 4 + J) * Nfp + b] = h->permG2C[maps[(size_t)mp * Nfp + S.T.facePos[J][b]]];
+                        }
                     h->bbPermOffset = (size_t)4 * Nfp + (size_t)M.nMaps * 4 * Nfp;
                     std::copy(h->permG2C.begin(), h->permG2C.end(), tab.begin() + h->bbPermOffset);
                     // the neighbour table once more with padded, 16-byte aligned rows (the trace gathers of stage_bb2 load a row with 128-bit loads)
@@ -597,7 +601,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                     h->dBBTab = devUpload(tab);
                     M.bbTab = h->dBBTab;
                     M.bbNbr16 = h->dBBTab + nbr16Offset;  // cudaMalloc returns 256-byte aligned memory
-                    for (int J = 0; J < 4; ++J) M.bbFaceLf[J] = S.T.faceLf[J];
+                    for (int J = 0; J < Nf; ++J) M.bbFaceLf[J] = S.T.faceLf[J];
                     std::vector<double> VC((size_t)Np * Np), VinvC((size_t)Np * Np);
                     for (int n = 0; n < Np; ++n)
                         for (int i = 0; i < Np; ++i) {
@@ -1615,7 +1619,9 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
                 if (!h->ws.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "no warp-specialised kernel for this dim/order/mean flow");
                 h->active = h->ws;
             } else if (value == 4 || value == 5) {  // 5: the face-sequential schedule of the same arithmetic
-                if (!h->bbKernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
+                if (!h->bbKernel.launch)
+                    throw DgbException(DGB_ERR_UNSUPPORTED, "first-generation Bernstein-Bezier kernel unavailable: " +
+                                                                (h->bbWhyNot.empty() ? std::string("tetrahedra of orders 2..5 only (kernel 6 covers this mesh)") : h->bbWhyNot));
                 h->active = value == 4 ? h->bbKernel : h->bbSeqKernel;
             } else if (value == 6) {
                 if (!h->bb2Kernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);

@@ -39,9 +39,10 @@ namespace {
 
 constexpr int kTE2 = 8;  // elements per tile: 8 elements x 4 fields = the 32 lanes of the warp
 
-template <int P>
+template <int DIM, int P>
 struct BB2Cfg {
-    static constexpr int NP = bb::tet(P), NFP = bb::tri(P);
+    typedef bb::Simplex<DIM, P> SX;
+    static constexpr int NP = SX::NP, NFP = SX::NFP, NF = DIM + 1;
     // Element stride of a state tile in shared memory (doubles). Lane (element, field) reads coefficient i of its element at
     // el*ES + i*4 + field: the four elements of a half-warp must start 4 (mod 8) doubles apart to hit disjoint 8-word bank windows. Np*4 does
     // at order 4 (140) — the tile is then one contiguous run, ONE bulk copy — but not at orders 3 and 5 (80 and 224 doubles: every
@@ -101,47 +102,49 @@ __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group
 __device__ __forceinline__ void cpWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Volume term of field q of one element whose coefficients lie interleaved ([coefficient][4 fields], canonical order) at
-// col: the same arithmetic as bb::fieldVolume.
-template <int N>
+// col: the same arithmetic as bb::fieldVolume, for tetrahedra and triangles (on triangles v_z has no coupling term).
+template <int DIM, int N>
 __device__ __forceinline__ void fieldVolumeInterleaved(int q, const double* col, const double (&gl)[4][3], const double (&v0)[3], bool flow, double rc2,
-                                                       double invRho, double (&out)[bb::tet(N)]) {
-    constexpr int NP = bb::tet(N), ND = bb::tet(N - 1);
+                                                       double invRho, double (&out)[bb::Simplex<DIM, N>::NP]) {
+    typedef bb::Simplex<DIM, N> SX;
+    constexpr int NP = SX::NP, ND = SX::ND, NV = SX::NV;
     double t[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) t[i] = 0.0;
-    const int nCoupling = q == 0 ? 3 : 1;
+    const int nCoupling = q == 0 ? DIM : q <= DIM ? 1 : 0;
     const int nPass = nCoupling + (flow ? 1 : 0);
     for (int pass = 0; pass < nPass; ++pass) {  // run-time trip count: one copy of the body
         int field;
-        double w[4];
+        double w[NV];
         if (pass < nCoupling) {
             field = q == 0 ? 1 + pass : 0;
             const int x = q == 0 ? pass : q - 1;
             const double s = q == 0 ? rc2 : invRho;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = s * (x == 0 ? gl[j][0] : x == 1 ? gl[j][1] : gl[j][2]);
+            for (int j = 0; j < NV; ++j) w[j] = s * (x == 0 ? gl[j][0] : (x == 1 || DIM == 2) ? gl[j][1] : gl[j][2]);
         } else {
             field = q;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = v0[0] * gl[j][0] + v0[1] * gl[j][1] + v0[2] * gl[j][2];
+            for (int j = 0; j < NV; ++j) w[j] = DIM == 3 ? v0[0] * gl[j][0] + v0[1] * gl[j][1] + v0[2] * gl[j][2] : v0[0] * gl[j][0] + v0[1] * gl[j][1];
         }
         double cc[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) cc[i] = col[i * 4 + field];
-        bb::dirDeriv<N, true>(cc, w, t);
+        SX::dirDerivAcc(cc, w, t);
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) out[i] = 0.0;
-    bb::elevateAdd<N>(t, -1.0, out);
+    SX::elevate(t, -1.0, out);
 }
 
 // resident warps per SM the register allocation aims at (the shared memory of a warp allows about as many)
-__host__ __device__ constexpr int bb2WarpsPerSm(int p) { return p <= 2 ? 16 : p == 3 ? 12 : p == 4 ? 8 : 6; }
+__host__ __device__ constexpr int bb2WarpsPerSm(int np) { return np <= 3 ? 24 : np <= 10 ? 16 : np <= 21 ? 12 : np <= 35 ? 8 : 6; }
 
-template <int P>
-__global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
-    using C = BB2Cfg<P>;
-    constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES;
+template <int DIM, int P>
+__global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
+    using C = BB2Cfg<DIM, P>;
+    using SX = typename C::SX;
+    constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
     constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
     extern __shared__ __align__(128) unsigned char smemRaw2[];
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
@@ -198,16 +201,16 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
     __syncwarp();
 
     // face metadata (lane = (element, local face)) and inverse Jacobian (lane = (element, *)) of tile tt, clamped at the range end
-    auto loadMeta = [&](int tt, int& flags, int& nbr, double (&fg)[4], double (&G)[9]) {
+    auto loadMeta = [&](int tt, int& flags, int& nbr, double (&fg)[4], double (&G)[DIM * DIM]) {
         const int e = min(A.eBegin + tt * kTE2 + el, A.eEnd - 1);
-        const int ef = e * 4 + q;
+        const int ef = e * NF + min(q, NF - 1);  // triangles: the fourth lane of an element repeats face 2 (never selected)
         flags = M.fflags[ef];
         nbr = M.fnbr[ef];
         const double2 f0 = *reinterpret_cast<const double2*>(M.fgeo + (int64_t)ef * 4);
         const double2 f1 = *reinterpret_cast<const double2*>(M.fgeo + (int64_t)ef * 4 + 2);
-        fg[0] = f0.x; fg[1] = f0.y; fg[2] = f1.x; fg[3] = f1.y;
+        fg[0] = f0.x; fg[1] = f0.y; fg[2] = f1.x; fg[3] = f1.y * SX::FACE_SCALE;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) G[j] = M.Ginv[(int64_t)e * 9 + j];
+        for (int j = 0; j < DIM * DIM; ++j) G[j] = M.Ginv[(int64_t)e * (DIM * DIM) + j];
     };
     auto tileBytes = [&](int tt) { return (uint32_t)(min(kTE2, A.eEnd - (A.eBegin + tt * kTE2)) * NP * 32); };
     // Tile copies (warp-collective). Contiguous tiles: lane 0 moves the whole tile; padded tiles: lane l moves element l.
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
     };
 
     int flags, nbr;
-    double fg[4], G[9];
+    double fg[4], G[DIM * DIM];
     loadMeta(t, flags, nbr, fg, G);
     issueY(t);
     if (!haloReady && touchesBorder(t)) waitPeers();
@@ -285,16 +288,18 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
         }
         double gl[4][3];
 #pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            const double g0 = G[x * 3 + 0], g1 = G[x * 3 + 1], g2 = G[x * 3 + 2];
-            gl[0][x] = -(g0 + g1 + g2);
-            gl[1][x] = g0;
-            gl[2][x] = g1;
-            gl[3][x] = g2;
+        for (int x = 0; x < DIM; ++x) {
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < DIM; ++u) {
+                gl[1 + u][x] = G[x * DIM + u];
+                s = s + G[x * DIM + u];
+            }
+            gl[0][x] = -s;
         }
         // metadata of the next tile: requested now, consumed during the last face of this tile
         int flagsN = 0, nbrN = -1;
-        double fgN[4] = {0, 0, 0, 0}, GN[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double fgN[4] = {0, 0, 0, 0}, GN[DIM * DIM] = {};
         if (more) loadMeta(tn, flagsN, nbrN, fgN, GN);
         // acc is needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
         if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
@@ -307,10 +312,10 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
         __syncwarp();
 
         double out[NP];
-        fieldVolumeInterleaved<P>(q, sY + el * ES, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
+        fieldVolumeInterleaved<DIM, P>(q, sY + el * ES, gl, ph.v0, flow, ph.rc2, ph.invRho, out);
 
 #pragma unroll 1
-        for (int J = 0; J < 4; ++J) {
+        for (int J = 0; J < NF; ++J) {
             const int lf = M.bbFaceLf[J];
             // lift inputs of face J for this lane's (element, field), straight into registers. With a = own - neighbour
             // (boundary: the neighbour trace is zero), S = n . a_v, the reference's fluxes read (bb_ops.h: faceInput)
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
                 x[b] = A1 * a + (A2 * ap + A3 * S);
             }
             __syncwarp();  // the trace buffer is free: the next face's traces travel while this face is lifted
-            if (J < 3) issueTraces(J + 1, flags, nbr);
+            if (J < NF - 1) issueTraces(J + 1, flags, nbr);
             else {
                 // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
                 if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
@@ -351,12 +356,12 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
                 }
             }
             double zl[NP];
-            bb::liftFaceLocal<P>(x, zl);
+            SX::liftLocal(x, zl);
             switch (J) {  // warp-uniform
-                case 0: bb::scatterAddFace<P, 0>(zl, out); break;
-                case 1: bb::scatterAddFace<P, 1>(zl, out); break;
-                case 2: bb::scatterAddFace<P, 2>(zl, out); break;
-                default: bb::scatterAddFace<P, 3>(zl, out); break;
+                case 0: SX::template scatterAdd<0>(zl, out); break;
+                case 1: SX::template scatterAdd<1>(zl, out); break;
+                case 2: SX::template scatterAdd<2>(zl, out); break;
+                default: SX::template scatterAdd<3>(zl, out); break;
             }
         }
 
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
 #pragma unroll
         for (int j = 0; j < 4; ++j) fg[j] = fgN[j];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) G[j] = GN[j];
+        for (int j = 0; j < DIM * DIM; ++j) G[j] = GN[j];
     }
     bulkWaitAll();  // every store of this warp, local and remote, is complete
     if (fx != nullptr) {
@@ -442,19 +447,19 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(P)) stageBB2Kernel(DeviceMes
     }
 }
 
-template <int P>
+template <int DIM, int P>
 void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
-    using C = BB2Cfg<P>;
+    using C = BB2Cfg<DIM, P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
     static KernelConfig kc;
     static int perSm[kMaxDevices] = {};
-    const int numSm = configureKernel(kc, stageBB2Kernel<P>, C::SMEM, "stage_bb2");
+    const int numSm = configureKernel(kc, stageBB2Kernel<DIM, P>, C::SMEM, "stage_bb2");
     int dev = 0;
     cudaGetDevice(&dev);
     if (perSm[dev] == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stageBB2Kernel<P>, 32, C::SMEM) != cudaSuccess || n < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stageBB2Kernel<DIM, P>, 32, C::SMEM) != cudaSuccess || n < 1) {
             cudaGetLastError();
             throw UnsupportedError("stage_bb2: the kernel does not fit an SM of this device");
         }
@@ -462,7 +467,7 @@ void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     }
     const int nTiles = (nEl + kTE2 - 1) / kTE2;
     const int grid = std::max(1, std::min(nTiles, (numSm - std::min(A.smReserve, numSm / 2)) * perSm[dev]));
-    stageBB2Kernel<P><<<grid, 32, C::SMEM, s>>>(M, A, nTiles);
+    stageBB2Kernel<DIM, P><<<grid, 32, C::SMEM, s>>>(M, A, nTiles);
 }
 
 // nodal <-> Bernstein conversion between the field-major nodal layout u[q][el*Np + n] (the reference's, the C ABI's) and the
@@ -512,11 +517,10 @@ __global__ void packElementsBB2Kernel(const double* __restrict__ y, int per, con
 
 StageKernel selectBB2Kernel(int dim, int order) {
     StageKernel k;
-    if (dim != 3) return k;
-    if (order == 2) { k.launch = &launchBB2<2>; k.name = "stage_bb2<3,2>"; }
-    if (order == 3) { k.launch = &launchBB2<3>; k.name = "stage_bb2<3,3>"; }
-    if (order == 4) { k.launch = &launchBB2<4>; k.name = "stage_bb2<3,4>"; }
-    if (order == 5) { k.launch = &launchBB2<5>; k.name = "stage_bb2<3,5>"; }
+#define DGB_BB2(D, P) if (dim == D && order == P) { k.launch = &launchBB2<D, P>; k.name = "stage_bb2<" #D "," #P ">"; }
+    DGB_BB2(3, 1) DGB_BB2(3, 2) DGB_BB2(3, 3) DGB_BB2(3, 4) DGB_BB2(3, 5)
+    DGB_BB2(2, 1) DGB_BB2(2, 2) DGB_BB2(2, 3) DGB_BB2(2, 4) DGB_BB2(2, 5) DGB_BB2(2, 6)
+#undef DGB_BB2
     return k;
 }
 

@@ -13,7 +13,12 @@ TOL = 1e-10
 
 
 def _mesh(pkg, mesh_dir, name, order, v0):
-    model = pkg.Model.make_cube(int(name.split(":")[1]), -10.0, 10.0, order) if name.startswith("cube:") else pkg.Model.open_msh(mesh_dir / name, order)
+    if name.startswith("cube:"):
+        model = pkg.Model.make_cube(int(name.split(":")[1]), -10.0, 10.0, order)
+    elif name.startswith("square:"):
+        model = pkg.Model.make_square(int(name.split(":")[1]), -10.0, 10.0, order)
+    else:
+        model = pkg.Model.open_msh(mesh_dir / name, order)
     mesh = pkg.Mesh(model, pkg.Config())
     mesh.set_physics(c0=343.0, rho0=1.225, v0=v0, dt=0.1 * mesh.h_min() / (343.0 * (2 * order + 1)))
     b = np.nonzero(mesh.fIsBoundary)[0]
@@ -60,6 +65,78 @@ def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     orc.run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, want, 0.0, 12)
     for q in range(4):
         assert rel_l2(got[q], want[q]) < TOL
+    eng.close()
+
+
+# second-generation kernel only: triangles of orders 1..6 (the reference's 2D meshes, a refined square with partial tiles) and tetrahedra of order 1
+CASES2 = [("square.msh", 1, (0.0, 0.0, 0.0)), ("square:5", 1, (30.0, 10.0, 0.0)), ("disk.msh", 2, (0.0, 0.0, 0.0)), ("square_reflection.msh", 3, (30.0, 10.0, 0.0)),
+          ("square.msh", 4, (0.0, 0.0, 0.0)), ("square:3", 5, (3.0, -2.0, 0.0)), ("disk.msh", 6, (0.0, 0.0, 0.0)), ("cube:3", 1, (0.0, 0.0, 0.0)),
+          ("sphere.msh", 1, (30.0, 10.0, 5.0))]
+
+
+@pytest.mark.parametrize("name,order,v0", CASES2)
+def test_rhs_and_rk4_triangles_and_order_1(pkg, oracle_mod, mesh_dir, name, order, v0):
+    mesh = _mesh(pkg, mesh_dir, name, order, v0)
+    u0 = _state(mesh)
+    orc = oracle_mod.Oracle(mesh)
+    eng = pkg.Engine(mesh, options={"kernel": 6})
+    assert eng.kernel_name == f"stage_bb2<{mesh.dim},{order}>"
+    rhs = eng.eval_rhs(u0)
+    ref = orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u0)
+    for q in range(4):
+        if np.abs(ref[q]).max() == 0:  # v_z on a 2D mesh without mean flow: L(u)_vz == 0, the Bernstein path leaves rounding noise
+            assert np.linalg.norm(rhs[q]) < 1e-10 * np.linalg.norm(u0[q]) * 343.0 / mesh.h_min()
+        else:
+            assert rel_l2(rhs[q], ref[q]) < TOL
+    eng.set_state(u0)
+    back = eng.get_state()
+    for q in range(4):
+        assert rel_l2(back[q], u0[q]) < 1e-13
+    t = eng.run(pkg.RUNGE_KUTTA, 0.0, 7)
+    eng.run(pkg.RUNGE_KUTTA, t, 5)
+    got = eng.get_state()
+    want = u0.copy()
+    orc.run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, want, 0.0, 12)
+    for q in range(4):
+        assert rel_l2(got[q], want[q]) < TOL
+    eng.run(pkg.EULER1, 0.0, 3)
+    got = eng.get_state()
+    orc.run(oracle_mod.Oracle.OPERATOR, pkg.EULER1, want, 0.0, 3)
+    for q in range(4):
+        assert rel_l2(got[q], want[q]) < TOL
+    eng.close()
+
+
+def test_sources_probes_receivers_in_bernstein_mode_on_triangles(pkg, oracle_mod, mesh_dir):
+    model = pkg.Model.open_msh(mesh_dir / "square.msh", 3)
+    cfg = pkg.Config()
+    cfg.add_source(2.0, 1.0, 0.0, 1.0, 10.0, 1500.0, 0.3, 1.0)
+    mesh = pkg.Mesh(model, cfg)
+    mesh.set_physics(c0=343.0, rho0=1.225, v0=(0.0, 0.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * 7))
+    offsets, idx = mesh.source_nodes()
+    assert len(idx) > 3
+    probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(3, 3, 0), int(idx[1])], dtype=np.int32)
+    el, w = mesh.locate_receivers([(0.3, -0.2, 0.0), (2.0, 2.5, 0.0)])
+    steps = 25
+    u0 = _state(mesh, 5) * 1e-2
+    eng = pkg.Engine(mesh, options={"kernel": 6})
+    assert eng.kernel_name == "stage_bb2<2,3>"
+    eng.set_sources_from_config()
+    eng.set_probes(probes)
+    eng.set_receivers(el, w)
+    eng.set_state(u0)
+    eng.run(pkg.RUNGE_KUTTA, 0.0, steps)
+    got, rec_p, rec_r = eng.get_state(), eng.get_probes(steps), eng.get_receivers(steps)
+    orc = oracle_mod.Oracle(mesh)
+    orc.set_sources_from_config()
+    orc.set_receivers(el, w)
+    want = u0.copy()
+    _, ref_p = orc.run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, want, 0.0, steps, probes)
+    ref_r = orc.get_receivers(steps)
+    for q in range(3):
+        assert rel_l2(got[q], want[q]) < TOL
+        assert rel_l2(rec_p[:, :, q], ref_p[:, :, q]) < TOL
+        assert rel_l2(rec_r[:, :, q], ref_r[:, :, q]) < TOL
     eng.close()
 
 
@@ -126,8 +203,13 @@ def test_unsupported_combinations_fail_loudly(pkg, mesh_dir):
     mesh2 = pkg.Mesh(pkg.Model.open_msh(mesh_dir / "square.msh", 2), pkg.Config())
     eng2 = pkg.Engine(mesh2)
     with pytest.raises(pkg.DgbError):
-        eng2.set_option("kernel", 4)  # triangles: no Bernstein kernel
+        eng2.set_option("kernel", 4)  # triangles: no first-generation Bernstein kernel
     eng2.close()
+    mesh1 = pkg.Mesh(pkg.Model.open_msh(mesh_dir / "line.msh", 1), pkg.Config())
+    eng1 = pkg.Engine(mesh1)
+    with pytest.raises(pkg.DgbError):
+        eng1.set_option("kernel", 6)  # lines: no Bernstein kernel at all
+    eng1.close()
     mesh6 = pkg.Mesh(pkg.Model.make_cube(2, -10.0, 10.0, 6), pkg.Config())
     eng6 = pkg.Engine(mesh6)
     with pytest.raises(pkg.DgbError):
