@@ -135,7 +135,7 @@ struct dgb_handle {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evBorder = nullptr, evRecv = nullptr;
     std::vector<cudaEvent_t> stageEv;  // pairs, for per-launch timing of the stage kernel
     int stageEvUsed = 0;
-    StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, bb2Kernel, active;
+    StageKernel generic, tiled, ws, bbKernel, bbSeqKernel, bb2Kernel, bbeKernel, active;
     // Bernstein-Bezier mode (dgb_set_option("kernel", 4)): the state arrays hold Bernstein coefficients; V / V^-1 convert
     int bbMode = 0;                  // representation of the resident state: 0 nodal, 1 coefficients [field][el][mesh node order] (stage_bb.cu),
                                      // 2 coefficients [el][canonical index][field] (stage_bb2.cu)
@@ -162,9 +162,14 @@ struct dgb_handle {
     int32_t *dSrcElList = nullptr, *dSrcNodeOff = nullptr, *dSrcNodeLocal = nullptr;
     // Measured on B200 (profiles/r02_order_sweep.json): the second-generation Bernstein kernel beats the CUDA-core kernel on
     // tetrahedra from order 2 on and the dense DMMA kernels at orders 3 / 4, with and without mean flow
-    // measured (profiles/r02_order_sweep.json): the second-generation Bernstein kernel wins on triangles of every order and on tetrahedra
-    // of order >= 2; tetrahedra of order 1 keep the generic kernel
-    StageKernel autoKernel() const { return (bb2Kernel.launch && (M.order >= 2 || M.dim == 2) && preferBB2) ? bb2Kernel : ws.launch ? ws : tiled.launch ? tiled : generic; }
+    // measured (profiles/r02_order_sweep.json): Bernstein kernels win wherever they exist — one thread per element (stage_bbe) on
+    // triangles of orders 1 / 2 and tetrahedra of order 1, the (element, field) pipeline (stage_bb2) on triangles of orders 3..6
+    // and tetrahedra of orders 2..5
+    StageKernel autoKernel() const {
+        if (preferBB2 && bbeKernel.launch && ((M.dim == 2 && M.order <= 2) || (M.dim == 3 && M.order == 1))) return bbeKernel;
+        if (preferBB2 && bb2Kernel.launch) return bb2Kernel;
+        return ws.launch ? ws : tiled.launch ? tiled : generic;
+    }
     bool preferBB2 = true;
     int overlap = -1;   // 0: stage, then exchange; 1: border, [exchange || interior]; 2: interior(s+1) || exchange(s), then border; -1: automatic
     int smReserve = 4;  // SMs left to the NCCL kernels while an overlapped interior launch of a persistent kernel runs
@@ -577,6 +582,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                 }
                 // second generation: canonical coefficient order, interleaved fields
                 h->bb2Kernel = bb2Candidate;
+                h->bbeKernel = selectBBEKernel(dim, d->order);  // same representation, one thread per element (lowest orders)
                 {
                     h->permG2C.assign(Np, 0);
                     for (int i = 0; i < Np; ++i) h->permG2C[S.T.permC2G[i]] = (uint8_t)i;
@@ -615,6 +621,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
                 h->bbWhyNot = e.what();
                 h->bbKernel = StageKernel{};
                 h->bb2Kernel = StageKernel{};
+                h->bbeKernel = StageKernel{};
             }
         }
 
@@ -1024,7 +1031,7 @@ void finishExchange(dgb_handle* h) {
 // Representation of the resident state a stage kernel works on (dgb_handle::bbMode)
 int representationOf(const dgb_handle* h, const StageKernel& k) {
     if (!k.launch) return 0;
-    if (k.launch == h->bb2Kernel.launch) return 2;
+    if (k.launch == h->bb2Kernel.launch || k.launch == h->bbeKernel.launch) return 2;
     if (k.launch == h->bbKernel.launch || k.launch == h->bbSeqKernel.launch) return 1;
     return 0;
 }
@@ -1626,6 +1633,11 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             } else if (value == 6) {
                 if (!h->bb2Kernel.launch) throw DgbException(DGB_ERR_UNSUPPORTED, "Bernstein-Bezier kernel unavailable: " + h->bbWhyNot);
                 h->active = h->bb2Kernel;
+            } else if (value == 7) {
+                if (!h->bbeKernel.launch)
+                    throw DgbException(DGB_ERR_UNSUPPORTED, "element-per-thread Bernstein-Bezier kernel unavailable: " +
+                                                                (h->bbWhyNot.empty() ? std::string("triangles of orders 1..3 and tetrahedra of order 1 only") : h->bbWhyNot));
+                h->active = h->bbeKernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes
             if (h->curved) h->curvedName = h->firstCurved > 0 ? std::string(h->active.name) + " + stage_curved" : std::string("stage_curved");
@@ -1678,7 +1690,7 @@ int dgb_get_option(dgb_handle* h, const char* key, int* value) {
         if (!h || !key || !value) throw DgbException(DGB_ERR_ARG, "null argument");
         const std::string k(key);
         auto is = [&](const StageKernel& s) { return s.launch && h->active.launch == s.launch; };
-        if (k == "kernel") *value = is(h->bb2Kernel) ? 6 : is(h->bbSeqKernel) ? 5 : is(h->bbKernel) ? 4 : is(h->ws) ? 3 : is(h->tiled) ? 2 : 1;
+        if (k == "kernel") *value = is(h->bbeKernel) ? 7 : is(h->bb2Kernel) ? 6 : is(h->bbSeqKernel) ? 5 : is(h->bbKernel) ? 4 : is(h->ws) ? 3 : is(h->tiled) ? 2 : 1;
         else if (k == "exchange") *value = h->partitioned ? h->exchangeMode : 0;
         else if (k == "representation") *value = h->bbMode;
         else if (k == "overlap") *value = h->partitioned ? overlapMode(h) : 0;

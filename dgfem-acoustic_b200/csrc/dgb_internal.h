@@ -107,6 +107,8 @@ void launchSetNodesBB(double* field, int Np, const int32_t* elList, const int32_
                       const double* V, const double* Vinv, cudaStream_t s, int coefStride = 1, const uint8_t* perm = nullptr);
 // second-generation Bernstein kernel (stage_bb2.cu): interleaved canonical coefficient layout c[(el*Np + i)*4 + q]
 StageKernel selectBB2Kernel(int dim, int order);
+// the same representation, one thread per element (stage_bbe.cu): triangles of orders 1..3, tetrahedra of order 1
+StageKernel selectBBEKernel(int dim, int order);
 void launchConvertBB2(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, bool toBB, cudaStream_t s);
 void launchPackElementsBB2(const double* y, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s);
 // y = Mat x per element and field over a whole state array (nodal <-> Bernstein conversion); in and out may alias

@@ -29,6 +29,7 @@
 // Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded at orders 2 / 3 / 5) | one face's traces |
 // face coefficients | 3 mbarriers.
 #include "bb_ops.h"
+#include "dgb_async.cuh"
 #include "dgb_device.cuh"
 #include "dgb_internal.h"
 #include "dgb_launch.h"
@@ -59,47 +60,6 @@ struct BB2Cfg {
     static constexpr size_t SMEM = (size_t)(2 * TILE + kTE2 * TRS + 32 * FCS) * sizeof(double) + 4 * sizeof(unsigned long long);
     static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
 };
-
-__device__ __forceinline__ uint32_t sAddr2(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit2(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sAddr2(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sAddr2(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait2(unsigned long long* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(sAddr2(bar)), "r"(parity)
-                     : "memory");
-    }
-}
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sAddr2(smemDst)),
-                 "l"(__cvta_generic_to_global(gmemSrc)), "r"(bytes), "r"(sAddr2(bar))
-                 : "memory");
-}
-// TMA bulk copy shared -> global (bulk async-group)
-__device__ __forceinline__ void bulkStore(void* gmemDst, const void* smemSrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gmemDst)), "r"(sAddr2(smemSrc)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulkPrefetchL2(const void* gmemSrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gmemSrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 16-byte asynchronous copy that bypasses L1 (a trace sector is used once); srcBytes == 0 writes zeros
-__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc, uint32_t srcBytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sAddr2(smemDst)), "l"(__cvta_generic_to_global(gmemSrc)), "r"(srcBytes) : "memory");
-}
-__device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cpWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Volume term of field q of one element whose coefficients lie interleaved ([coefficient][4 fields], canonical order) at
 // col: the same arithmetic as bb::fieldVolume, for tetrahedra and triangles (on triangles v_z has no coupling term).
@@ -306,7 +266,9 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         if (lane == 0 && more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
         // u can only be requested when the last face has read the stage-input tile it replaces (one lift before it is needed):
         // bring it to L2 now, so that the request finds it there
+#ifdef DGB_BB2_UPREFETCH  // measured: 1.615 ms per stage with it, 1.585 without (config 5) — off
         if (lane == 0 && loadU && mode != MODE_RK1) bulkPrefetchL2(uSrc + (int64_t)e0 * NP * 4, bytes);
+#endif
         mbarWait2(&bars[0], phY);
         phY ^= 1;
         __syncwarp();

@@ -12,8 +12,9 @@ model = pkg.Model.open_msh(tmp, 1)
 cfg = model.parse_config(Path("/root/repo/tests/golden/configs/square_pulse.conf"))
 mesh = pkg.Mesh(model, cfg)
 u0 = mesh.initial_condition()
-for mode in (0, 1, 0, 1):
-    eng = pkg.Engine(mesh)
+kernels = [int(a) for a in sys.argv[1:]] or [0]
+for kernel, mode in [(k, m) for k in kernels for m in (0, 1, 0, 1)]:
+    eng = pkg.Engine(mesh, options={"kernel": kernel})
     eng.set_option("graph", mode)
     eng.set_state(u0)
     eng.run(pkg.RUNGE_KUTTA, 0.0, 50)

@@ -74,13 +74,17 @@ CASES2 = [("square.msh", 1, (0.0, 0.0, 0.0)), ("square:5", 1, (30.0, 10.0, 0.0))
           ("sphere.msh", 1, (30.0, 10.0, 5.0))]
 
 
-@pytest.mark.parametrize("name,order,v0", CASES2)
-def test_rhs_and_rk4_triangles_and_order_1(pkg, oracle_mod, mesh_dir, name, order, v0):
+# element-per-thread kernel (stage_bbe.cu, kernel 7): triangles of orders 1..3, tetrahedra of order 1
+CASES_E = [(n, o, v, 7) for (n, o, v) in CASES2 if o <= 3 and not (o > 1 and n.startswith(("cube", "sphere")))] + [("square:7", 2, (30.0, 10.0, 0.0), 7)]
+
+
+@pytest.mark.parametrize("name,order,v0,variant", [(n, o, v, 6) for (n, o, v) in CASES2] + CASES_E)
+def test_rhs_and_rk4_triangles_and_order_1(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
     mesh = _mesh(pkg, mesh_dir, name, order, v0)
     u0 = _state(mesh)
     orc = oracle_mod.Oracle(mesh)
-    eng = pkg.Engine(mesh, options={"kernel": 6})
-    assert eng.kernel_name == f"stage_bb2<{mesh.dim},{order}>"
+    eng = pkg.Engine(mesh, options={"kernel": variant})
+    assert eng.kernel_name == (f"stage_bb2<{mesh.dim},{order}>" if variant == 6 else f"stage_bbe<{mesh.dim},{order}>")
     rhs = eng.eval_rhs(u0)
     ref = orc.eval_rhs(oracle_mod.Oracle.OPERATOR, u0)
     for q in range(4):
@@ -107,7 +111,8 @@ def test_rhs_and_rk4_triangles_and_order_1(pkg, oracle_mod, mesh_dir, name, orde
     eng.close()
 
 
-def test_sources_probes_receivers_in_bernstein_mode_on_triangles(pkg, oracle_mod, mesh_dir):
+@pytest.mark.parametrize("variant", [6, 7])
+def test_sources_probes_receivers_in_bernstein_mode_on_triangles(pkg, oracle_mod, mesh_dir, variant):
     model = pkg.Model.open_msh(mesh_dir / "square.msh", 3)
     cfg = pkg.Config()
     cfg.add_source(2.0, 1.0, 0.0, 1.0, 10.0, 1500.0, 0.3, 1.0)
@@ -119,8 +124,8 @@ def test_sources_probes_receivers_in_bernstein_mode_on_triangles(pkg, oracle_mod
     el, w = mesh.locate_receivers([(0.3, -0.2, 0.0), (2.0, 2.5, 0.0)])
     steps = 25
     u0 = _state(mesh, 5) * 1e-2
-    eng = pkg.Engine(mesh, options={"kernel": 6})
-    assert eng.kernel_name == "stage_bb2<2,3>"
+    eng = pkg.Engine(mesh, options={"kernel": variant})
+    assert eng.kernel_name == ("stage_bb2<2,3>" if variant == 6 else "stage_bbe<2,3>")
     eng.set_sources_from_config()
     eng.set_probes(probes)
     eng.set_receivers(el, w)
