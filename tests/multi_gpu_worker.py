@@ -23,13 +23,15 @@ def main():
     flow = int(sys.argv[6]) if len(sys.argv) > 6 else 1  # 0: zero mean flow (warp-specialised kernel at orders 3, 4)
     exchange = int(sys.argv[7]) if len(sys.argv) > 7 else 0  # 1: direct peer-to-peer stores instead of ncclSend/ncclRecv
     kernel = int(sys.argv[8]) if len(sys.argv) > 8 else 0      # 4: Bernstein-Bezier kernel (every rank switches)
+    dim = int(sys.argv[9]) if len(sys.argv) > 9 else 3          # 2: refined square of triangles instead of the cube of tetrahedra
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = graft.load_package()
-    model = pkg.Model.make_cube(cells, -10.0, 10.0, order)
+    model = pkg.Model.make_cube(cells, -10.0, 10.0, order) if dim == 3 else pkg.Model.make_square(cells, -10.0, 10.0, order)
+    zs = 1.0 if dim == 3 else 0.0  # the square lies in z = 0
     cfg = pkg.Config()
-    cfg.add_initial_condition(1.0, -2.0, 0.5, 30.0, 1.0)
+    cfg.add_initial_condition(1.0, -2.0, 0.5 * zs, 30.0, 1.0)
     cfg.add_source(2.0, 1.0, 0.0, 6.0, 10.0, 1500.0, 0.0, 1.0)
     mesh = pkg.Mesh(model, cfg)
     mesh.set_physics(c0=343.0, rho0=1.225, v0=(30.0, 10.0, 0.0) if flow else (0.0, 0.0, 0.0), dt=0.1 * mesh.h_min() / (343.0 * (2 * order + 1)))
@@ -41,7 +43,7 @@ def main():
     if rank == 0:
         idt = torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(idt, 0)
-    probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5), mesh.nearest_node(-7, 3, -2)], dtype=np.int32)
+    probes = np.array([mesh.nearest_node(0, 0, 0), mesh.nearest_node(5, 5, 5 * zs), mesh.nearest_node(-7, 3, -2 * zs)], dtype=np.int32)
     u0 = mesh.initial_condition()
     eng = pkg.Engine(mesh, el_part=part, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes(), options={"overlap": overlap})
     if kernel:
@@ -52,7 +54,7 @@ def main():
     eng.set_sources_from_config()
     eng.set_probes(probes)
     # interpolated receivers in different parts of the cube: with 2 ranks at least one lies in an element of rank 1
-    r_el, r_w = mesh.locate_receivers([(-6.3, 2.2, 1.1), (6.1, -3.3, 0.4), (0.2, 7.7, -5.1), (1.3, -8.2, 6.6)])
+    r_el, r_w = mesh.locate_receivers([(-6.3, 2.2, 1.1 * zs), (6.1, -3.3, 0.4 * zs), (0.2, 7.7, -5.1 * zs), (1.3, -8.2, 6.6 * zs)])
     assert len(set(int(part[e]) for e in r_el)) > 1
     eng.set_receivers(r_el, r_w)
     pinned = cells % 2 == 1  # odd sizes: page-locked caller buffers (the GPU gathers / scatters them over PCIe), even: pageable (staged)

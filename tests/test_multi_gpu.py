@@ -40,15 +40,24 @@ def test_partitioned_equals_single_direct_exchange(tmp_path, world, cells, order
     _run_and_compare(tmp_path, world, cells, order, overlap, flow, 1, kernel)
 
 
-def _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, kernel=0, tol=1e-12):
+# Low orders and triangles: the automatic choice is the element-per-thread Bernstein kernel (triangles of orders 1 / 2, tetrahedra of order 1:
+# direct stores or NCCL, never the fused exchange) or stage_bb2 on triangles (fused exchange); dim 2 = refined square.
+@pytest.mark.parametrize("world,cells,order,overlap,flow,exchange,kernel,dim", [
+    (2, 7, 1, 0, 1, 0, 0, 3), (2, 7, 1, 1, 0, 2, 0, 3), (2, 24, 1, 0, 1, 2, 0, 2), (2, 24, 2, 1, 0, 0, 0, 2), (2, 24, 2, 0, 1, 1, 7, 2),
+    (2, 20, 3, 0, 1, 2, 0, 2), (2, 16, 4, 1, 0, 0, 0, 2), (2, 12, 6, 0, 1, 2, 0, 2), (2, 7, 1, 0, 1, 2, 6, 3)])
+def test_partitioned_equals_single_low_orders_and_triangles(tmp_path, world, cells, order, overlap, flow, exchange, kernel, dim):
+    _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, kernel, dim=dim)
+
+
+def _run_and_compare(tmp_path, world, cells, order, overlap, flow, exchange, kernel=0, tol=1e-12, dim=3):
     """The single-GPU run on rank 0 uses the same kernel as the partitioned run: the two must agree to rounding."""
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     worker = Path(__file__).resolve().parent / "multi_gpu_worker.py"
     steps = 12
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29000 + overlap * 7 + order + 20 * flow + cells + 100 * exchange + 200 * kernel), str(worker), str(tmp_path),
-           str(cells), str(order), str(steps), str(overlap), str(flow), str(exchange), str(kernel)]
+           "--master-port", str(29000 + overlap * 7 + order + 20 * flow + cells + 100 * exchange + 200 * kernel + 1500 * (dim == 2)), str(worker), str(tmp_path),
+           str(cells), str(order), str(steps), str(overlap), str(flow), str(exchange), str(kernel), str(dim)]
     subprocess.run(cmd, check=True, timeout=600)
     single = np.load(tmp_path / "single.npz")
     merged = np.zeros_like(single["u"])
