@@ -46,6 +46,7 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc, ui
 }
 __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cpWaitAllButOne() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 }  // namespace
 }  // namespace dgb

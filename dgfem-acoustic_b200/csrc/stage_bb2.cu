@@ -39,6 +39,15 @@ namespace dgb {
 namespace {
 
 constexpr int kTE2 = 8;  // elements per tile: 8 elements x 4 fields = the 32 lanes of the warp
+#ifndef DGB_BB2_ACC_GLOBAL
+#define DGB_BB2_ACC_GLOBAL 0  // 1 (experiment): acc is read / written straight from / to global memory in the epilogue (L2-prefetched); its tile buffer receives
+                              // u at the start of the tile and the stage-input buffer the NEXT tile's input after the last face: no wait for either.
+                              // Measured (profiles/r02/t_*): the 70 8-byte global accesses per thread cost far more than the two waits they remove —
+                              // tetrahedra of order 4: 1.85 vs 1.46 ms, order 5: 0.99 vs 0.77; triangles of order 3 / 4: 2..5 % faster. Off.
+#endif
+#ifndef DGB_BB2_TRACE_BUFFERS
+#define DGB_BB2_TRACE_BUFFERS 0  // 0: per configuration (BB2Cfg::NTB); 1 / 2: forced (experiments)
+#endif
 
 template <int DIM, int P>
 struct BB2Cfg {
@@ -56,8 +65,12 @@ struct BB2Cfg {
     static constexpr int TRS = NFP * 4;                // element stride of the trace buffer: the 64-bit reads of lane (element, field) are conflict free
     static constexpr int NIT = (NFP + 1) / 2;          // gather instructions per face: lane (element, slot) moves the 16-byte chunk 4*it + slot of its element's trace
     static constexpr int RS = (NFP + 15) / 16 * 16;    // row stride (bytes) of DeviceMesh::bbNbr16
-    static constexpr int FCS = 10;                     // doubles per (local face, element): app, aps, b, c, d, n (+2: conflict-free 128-bit reads)
-    static constexpr size_t SMEM = (size_t)(2 * TILE + kTE2 * TRS + 32 * FCS) * sizeof(double) + 4 * sizeof(unsigned long long);
+    static constexpr int FCS = 8;                      // doubles per (local face, element): app, aps, b, c, d, n (the quads of a quarter-warp read two records: no conflict)
+    // trace buffers: the traces of face s + NTB are in flight while face s is lifted. Measured (profiles/r02/s_*): two buffers win where the
+    // second one does not cost a resident warp (tetrahedra of order 3 / 4: 0.441 -> 0.434, 1.60 -> 1.48 ms; triangles), one wins at tetrahedra
+    // of order 2 / 5 (0.270 vs 0.275, 0.770 vs 0.817 ms)
+    static constexpr int NTB = DGB_BB2_TRACE_BUFFERS != 0 ? DGB_BB2_TRACE_BUFFERS : (DIM == 3 && (P == 2 || P == 5)) ? 1 : 2;
+    static constexpr size_t SMEM = (size_t)(2 * TILE + NTB * kTE2 * TRS + 32 * FCS) * sizeof(double) + 4 * sizeof(unsigned long long);
     static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
 };
 
@@ -106,11 +119,12 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     using SX = typename C::SX;
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
     constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
+    constexpr bool kAccGlobal = DGB_BB2_ACC_GLOBAL != 0;
     extern __shared__ __align__(128) unsigned char smemRaw2[];
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
-    double* const sT = sA + C::TILE;                         // [8][TRS]  traces of the current face
-    double* const sFc = sT + kTE2 * TRS;                     // [4][8][FCS] face coefficients of the tile
+    double* const sT = sA + C::TILE;                         // [NTB][8][TRS] traces of the faces in flight
+    double* const sFc = sT + C::NTB * kTE2 * TRS;            // [4][8][FCS] face coefficients of the tile
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sFc + 32 * C::FCS);  // [0] stage input, [1] u, [2] acc
 
     const int lane = threadIdx.x, el = lane >> 2, q = lane & 3;
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     // (element, slot) moves the 16-byte chunks 4*it + slot of ITS element's trace: chunk j is half j&1 of the 32-byte record
     // (4 fields) of trace coefficient j>>1. Everything that depends on the element — neighbour, pairing map, base address — is
     // formed once per face; an iteration is one byte extraction, one 64-bit multiply-add and the copy. Boundary faces copy zeros.
-    auto issueTraces = [&](int J, int flagsT, int nbrT) {
+    auto issueTraces = [&](int J, int flagsT, int nbrT, double* buf) {
         const int srcLane = (lane & ~3) | M.bbFaceLf[J];
         const int fl = __shfl_sync(FULL, flagsT, srcLane), nb = __shfl_sync(FULL, nbrT, srcLane);
         const bool interior = (fl & FLAG_BC_MASK) == FACE_INTERIOR && nb >= 0;
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         const int hb = (lane >> 1) & 1;
         const uint32_t selLo = 0x4440u | hb, selHi = 0x4440u | (2 + hb);  // byte 2*it + hb of the row, zero-extended
         const double* const base = A.yin + (int64_t)(interior ? nb : 0) * (NP * 4) + (lane & 1) * 2;
-        double* const dst = sT + el * TRS + (lane & 3) * 2;
+        double* const dst = buf + el * TRS + (lane & 3) * 2;
         const uint32_t sz = interior ? 16u : 0u;
 #pragma unroll
         for (int it = 0; it < C::NIT; ++it) {
@@ -226,7 +240,9 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     loadMeta(t, flags, nbr, fg, G);
     issueY(t);
     if (!haloReady && touchesBorder(t)) waitPeers();
-    issueTraces(0, flags, nbr);
+    issueTraces(0, flags, nbr, sT);
+    if constexpr (C::NTB == 2) issueTraces(1, flags, nbr, sT + kTE2 * TRS);
+    int tb = 0;  // which trace buffer the next face reads
     uint32_t phY = 0, phU = 0, phA = 0;
 
     for (;;) {
@@ -262,7 +278,12 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         double fgN[4] = {0, 0, 0, 0}, GN[DIM * DIM] = {};
         if (more) loadMeta(tn, flagsN, nbrN, fgN, GN);
         // acc is needed by the epilogue only; the stores of the previous tile have read sA (waited for before its stage input was requested)
-        if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
+        if constexpr (kAccGlobal) {
+            if (loadU) loadTile(sA, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);  // the previous tile's store has read the buffer (waited for at its end)
+            if (lane == 0 && loadA) bulkPrefetchL2(A.acc + (int64_t)e0 * NP * 4, bytes);
+        } else {
+            if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, bytes, &bars[2]);
+        }
         if (lane == 0 && more) bulkPrefetchL2(A.yin + (int64_t)(A.eBegin + tn * kTE2) * NP * 4, tileBytes(tn));  // the request at the tile boundary will be an L2 hit
         // u can only be requested when the last face has read the stage-input tile it replaces (one lift before it is needed):
         // bring it to L2 now, so that the request finds it there
@@ -293,11 +314,12 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                 A2 = q == 0 ? 0.0 : nv * c1.y;
                 A3 = q == 0 ? c0.y : nv * c2.x;
             }
-            cpWaitAll();
+            if constexpr (C::NTB == 2) cpWaitAllButOne(); else cpWaitAll();  // the traces of this face have landed (the next face's may still travel)
             __syncwarp();
             double x[NFP];
             const double* const own = sY + el * ES + q;
-            const double* const tr = sT + el * TRS + q;
+            double* const tbuf = sT + tb * (kTE2 * TRS);
+            const double* const tr = tbuf + el * TRS + q;
 #pragma unroll
             for (int b = 0; b < NFP; ++b) {
                 const double a = own[M.bbOwn[J][b] * 4] - tr[b * 4];
@@ -307,14 +329,30 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                 const double ap = __shfl_sync(FULL, a, 0, 4);
                 x[b] = A1 * a + (A2 * ap + A3 * S);
             }
-            __syncwarp();  // the trace buffer is free: the next face's traces travel while this face is lifted
-            if (J < NF - 1) issueTraces(J + 1, flags, nbr);
-            else {
-                // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
-                if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
-                if (more) {
-                    if (!haloReady && touchesBorder(tn)) waitPeers();
-                    issueTraces(0, flagsN, nbrN);
+            __syncwarp();  // this trace buffer is free: the traces of face (this + NTB) travel while this face and the next are lifted
+            if constexpr (C::NTB == 2) {
+                tb ^= 1;
+                const int Jn = J + 2;  // face index in the sequence of this tile's faces followed by the next tile's
+                if (Jn < NF) issueTraces(Jn, flags, nbr, tbuf);
+                else if (more) {
+                    if (Jn == NF && !haloReady && touchesBorder(tn)) waitPeers();
+                    issueTraces(Jn - NF, flagsN, nbrN, tbuf);
+                } else cpCommit();  // an empty group keeps "all but the most recent group" uniform to the last face
+                // every read of the stage-input tile is done: the tile now receives u (or, with acc in global memory, the next tile's input)
+                if (J == NF - 1) {
+                    if constexpr (kAccGlobal) { if (more) issueY(tn); }
+                    else if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+                }
+            } else {
+                if (J < NF - 1) issueTraces(J + 1, flags, nbr, tbuf);
+                else {
+                    // every read of the stage-input tile is done: the tile now receives u; the next tile's first traces start
+                    if constexpr (kAccGlobal) { if (more) issueY(tn); }
+                    else if (loadU) loadTile(sY, uSrc + (int64_t)e0 * NP * 4, bytes, &bars[1]);
+                    if (more) {
+                        if (!haloReady && touchesBorder(tn)) waitPeers();
+                        issueTraces(0, flagsN, nbrN, tbuf);
+                    }
                 }
             }
             double zl[NP];
@@ -329,6 +367,38 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
 
         // fused RK update in the shared-memory tiles of the RK registers, then bulk stores
         if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
+        if constexpr (kAccGlobal) {
+            double* const pu = sA + el * ES + q;
+            const bool valid = e0 + el < A.eEnd;
+            double* const ga = A.acc + ((int64_t)min(e0 + el, A.eEnd - 1) * NP) * 4 + q;
+            const double dt = A.dt;
+            switch (mode) {
+                case MODE_RK1:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); if (valid) __stcg(ga + i * 4, k); pu[i * 4] = pu[i * 4] + 0.5 * k; }
+                    break;
+                case MODE_RK2:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); const double a = __ldcg(ga + i * 4) + 2 * k; if (valid) __stcg(ga + i * 4, a); pu[i * 4] = pu[i * 4] + 0.5 * k; }
+                    break;
+                case MODE_RK3:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); const double a = __ldcg(ga + i * 4) + 2 * k; if (valid) __stcg(ga + i * 4, a); pu[i * 4] = pu[i * 4] + k; }
+                    break;
+                case MODE_RK4:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pu[i * 4] = fma(__ldcg(ga + i * 4) + k, 1.0 / 6.0, pu[i * 4]); }
+                    break;
+                case MODE_EULER:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) pu[i * 4] = pu[i * 4] + __dmul_rn(dt, out[i]);
+                    break;
+                default:
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) pu[i * 4] = out[i];
+                    break;
+            }
+        } else {
         if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
         {
             double* const pu = sY + el * ES + q;
@@ -361,11 +431,11 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                     break;
             }
         }
+        }
         fenceProxyAsync();
         __syncwarp();
-        storeTile(uDst + (int64_t)e0 * NP * 4, sY, bytes);
-        if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
-        bulkCommit();
+        double* const sUt = kAccGlobal ? sA : sY;  // the tile that holds the updated u
+        storeTile(uDst + (int64_t)e0 * NP * 4, sUt, bytes);
         if (fx != nullptr && touchesBorder(t)) {
             // lane l ships element l of the tile to every peer that holds it as a halo element: one bulk store per target,
             // straight from the shared-memory tile over NVLink
@@ -373,14 +443,15 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
             if (lane < (int)(bytes / (NP * 32)) && k >= 0) {
                 const int p1 = fx->pushOff[k + 1];
                 for (int p = fx->pushOff[k]; p < p1; ++p)
-                    bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sY + lane * ES, NP * 32);
-                bulkCommit();
+                    bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sUt + lane * ES, NP * 32);
             }
         }
+        if constexpr (!kAccGlobal) { if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, bytes); }
+        bulkCommit();
         if (more) {
-            bulkWaitRead();  // both tiles have been read by the stores (every lane waits for the copies it issued)
+            bulkWaitRead();  // the tiles have been read by the stores (every lane waits for the copies it issued)
             __syncwarp();
-            issueY(tn);
+            if constexpr (!kAccGlobal) issueY(tn);
         }
         if (!more) break;
         t = tn;
