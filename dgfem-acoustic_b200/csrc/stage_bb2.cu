@@ -66,10 +66,10 @@ struct BB2Cfg {
     static constexpr int NIT = (NFP + 1) / 2;          // gather instructions per face: lane (element, slot) moves the 16-byte chunk 4*it + slot of its element's trace
     static constexpr int RS = (NFP + 15) / 16 * 16;    // row stride (bytes) of DeviceMesh::bbNbr16
     static constexpr int FCS = 8;                      // doubles per (local face, element): app, aps, b, c, d, n (the quads of a quarter-warp read two records: no conflict)
-    // trace buffers: the traces of face s + NTB are in flight while face s is lifted. Measured (profiles/r02/s_*): two buffers win where the
-    // second one does not cost a resident warp (tetrahedra of order 3 / 4: 0.441 -> 0.434, 1.60 -> 1.48 ms; triangles), one wins at tetrahedra
-    // of order 2 / 5 (0.270 vs 0.275, 0.770 vs 0.817 ms)
-    static constexpr int NTB = DGB_BB2_TRACE_BUFFERS != 0 ? DGB_BB2_TRACE_BUFFERS : (DIM == 3 && (P == 2 || P == 5)) ? 1 : 2;
+    // trace buffers: the traces of face s + NTB are in flight while face s is lifted. Measured (profiles/r02/s_*, u_*): two buffers win at
+    // tetrahedra of order 3 / 4 (0.441 -> 0.434, 1.60 -> 1.48 ms) and triangles of order 4 / 5 / 6 (1..3 %), one wins where the second costs a
+    // resident warp or the lift is too short to matter (tetrahedra of order 1 / 2 / 5, triangles of order 1..3)
+    static constexpr int NTB = DGB_BB2_TRACE_BUFFERS != 0 ? DGB_BB2_TRACE_BUFFERS : ((DIM == 3 && (P == 3 || P == 4)) || (DIM == 2 && P >= 4)) ? 2 : 1;
     static constexpr size_t SMEM = (size_t)(2 * TILE + NTB * kTE2 * TRS + 32 * FCS) * sizeof(double) + 4 * sizeof(unsigned long long);
     static_assert((TILE * 8) % 128 == 0 && (TRS * 8) % 16 == 0, "bulk-copy and 128-bit alignment of the shared-memory tiles");
 };
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     using C = BB2Cfg<DIM, P>;
     using SX = typename C::SX;
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
-    constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
     constexpr bool kAccGlobal = DGB_BB2_ACC_GLOBAL != 0;
+    constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
     extern __shared__ __align__(128) unsigned char smemRaw2[];
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
@@ -132,9 +132,11 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     const Phys ph = makePhys(M);
     const bool flow = ph.v0[0] != 0.0 || ph.v0[1] != 0.0 || ph.v0[2] != 0.0;
     const int mode = A.mode;
-    const bool loadU = mode != MODE_RHS, loadA = mode == MODE_RK2 || mode == MODE_RK3 || mode == MODE_RK4;
+    // u is reloaded over the stage-input tile after the last face; in the first RK stage and in an Euler step the stage input IS u: the tile stays
+    const bool loadU = kAccGlobal ? mode != MODE_RHS : (mode == MODE_RK2 || mode == MODE_RK3 || mode == MODE_RK4);
+    const bool loadA = mode == MODE_RK2 || mode == MODE_RK3 || mode == MODE_RK4;
     const bool storeA = mode == MODE_RK1 || mode == MODE_RK2 || mode == MODE_RK3;
-    const double* const uSrc = mode == MODE_EULER ? A.yin : A.u;  // first RK stage: u is the stage input (an L2 hit)
+    const double* const uSrc = mode == MODE_EULER ? A.yin : A.u;
     double* const uDst = mode == MODE_RK4 ? A.u : A.yout;
 
     // fused halo exchange (partitioned handles): the tiles that hold cut-adjacent elements come last (interior-first
@@ -366,8 +368,8 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         }
 
         // fused RK update in the shared-memory tiles of the RK registers, then bulk stores
-        if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
         if constexpr (kAccGlobal) {
+            if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
             double* const pu = sA + el * ES + q;
             const bool valid = e0 + el < A.eEnd;
             double* const ga = A.acc + ((int64_t)min(e0 + el, A.eEnd - 1) * NP) * 4 + q;
@@ -399,36 +401,45 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                     break;
             }
         } else {
+        // Two passes: what needs only acc first (k in place of out, the acc tile updated and on its way back), then — u is requested last and may
+        // still be travelling — what needs u. The arithmetic is that of the one-pass form (RK4: fma(acc + k, 1/6, u)).
         if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
         {
             double* const pu = sY + el * ES + q;
             double* const pa = sA + el * ES + q;
             const double dt = A.dt;
-            switch (mode) {
-                case MODE_RK1:
+            if (mode == MODE_RK1) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = k; pu[i * 4] = pu[i * 4] + 0.5 * k; }
-                    break;
-                case MODE_RK2:
+                for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); out[i] = k; pa[i * 4] = k; }
+            } else if (mode == MODE_RK2 || mode == MODE_RK3) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = pa[i * 4] + 2 * k; pu[i * 4] = pu[i * 4] + 0.5 * k; }
-                    break;
-                case MODE_RK3:
+                for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); out[i] = k; pa[i * 4] = pa[i * 4] + 2 * k; }
+            } else if (mode == MODE_RK4) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pa[i * 4] = pa[i * 4] + 2 * k; pu[i * 4] = pu[i * 4] + k; }
-                    break;
-                case MODE_RK4:
+                for (int i = 0; i < NP; ++i) out[i] = pa[i * 4] + __dmul_rn(dt, out[i]);
+            } else if (mode == MODE_EULER) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) { const double k = __dmul_rn(dt, out[i]); pu[i * 4] = fma(pa[i * 4] + k, 1.0 / 6.0, pu[i * 4]); }
-                    break;
-                case MODE_EULER:
+                for (int i = 0; i < NP; ++i) out[i] = __dmul_rn(dt, out[i]);
+            }
+            if (storeA) {
+                fenceProxyAsync();
+                __syncwarp();
+                storeTile(A.acc + (int64_t)e0 * NP * 4, sA, bytes);
+                bulkCommit();
+            }
+            if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
+            if (mode == MODE_RK1 || mode == MODE_RK2) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) pu[i * 4] = pu[i * 4] + __dmul_rn(dt, out[i]);
-                    break;
-                default:
+                for (int i = 0; i < NP; ++i) pu[i * 4] = pu[i * 4] + 0.5 * out[i];
+            } else if (mode == MODE_RK3 || mode == MODE_EULER) {
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) pu[i * 4] = out[i];
-                    break;
+                for (int i = 0; i < NP; ++i) pu[i * 4] = pu[i * 4] + out[i];
+            } else if (mode == MODE_RK4) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) pu[i * 4] = fma(out[i], 1.0 / 6.0, pu[i * 4]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) pu[i * 4] = out[i];
             }
         }
         }
@@ -446,8 +457,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                     bulkStore(fx->arr[A.fxWhich][fx->pushPeer[p]] + (int64_t)fx->pushSlot[p] * NP * 4, sUt + lane * ES, NP * 32);
             }
         }
-        if constexpr (!kAccGlobal) { if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, bytes); }
-        bulkCommit();
+        bulkCommit();  // (the acc tile left in the first pass of the epilogue)
         if (more) {
             bulkWaitRead();  // the tiles have been read by the stores (every lane waits for the copies it issued)
             __syncwarp();
