@@ -1636,7 +1636,7 @@ int dgb_set_option(dgb_handle* h, const char* key, int value) {
             } else if (value == 7) {
                 if (!h->bbeKernel.launch)
                     throw DgbException(DGB_ERR_UNSUPPORTED, "element-per-thread Bernstein-Bezier kernel unavailable: " +
-                                                                (h->bbWhyNot.empty() ? std::string("triangles of orders 1..3 and tetrahedra of order 1 only") : h->bbWhyNot));
+                                                                (h->bbWhyNot.empty() ? std::string("triangles of orders 1..3 and tetrahedra of orders 1 / 2 only") : h->bbWhyNot));
                 h->active = h->bbeKernel;
             } else h->active = h->autoKernel();
             // the Bernstein kernel keeps the state as Bernstein coefficients: convert what is resident when the representation changes

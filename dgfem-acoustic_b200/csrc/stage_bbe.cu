@@ -26,6 +26,9 @@ namespace dgb {
 namespace {
 
 constexpr int kTEE = 32;  // elements per tile = lanes
+#ifndef DGB_BBE_CONTIG
+#define DGB_BBE_CONTIG(NP) ((NP) == 3 || (NP) == 6 || (NP) == 10)
+#endif
 #ifndef DGB_BBE_WARPS
 #define DGB_BBE_WARPS(NP) ((NP) <= 3 ? 12 : (NP) <= 4 ? 10 : (NP) <= 6 ? 8 : 6)
 #endif
@@ -37,9 +40,9 @@ struct BBECfg {
     // Measured on B200 (profiles/r02/): with one bulk copy per element (padded, conflict-free rows) the kernel is bound by the
     // REQUEST RATE of the copy engine (160 requests of 96..192 bytes per tile: 0.58 / 0.59 of the HBM roof on triangles of order
     // 1 / 2); with ONE bulk copy per tile and array into unpadded rows the 128-bit accesses of the 32 lanes conflict 2-way
-    // (Np = 3) or 4-way (Np = 6) and the kernel reaches 0.83 / 0.71. Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way
-    // conflicts, 0.46) and Np = 10 keep the padded rows (0.57 / 0.56).
-    static constexpr bool CONTIG = NP == 3 || NP == 6;
+    // (Np = 3) or 4-way (Np = 6, 10) and the kernel reaches 0.83 / 0.71 (Np = 10: 0.56 -> 0.60, tetrahedra of order 2: 0.47 either way —
+    // stage_bb2 is the better kernel at Np = 10). Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way conflicts, 0.46) keeps the padded rows (0.57).
+    static constexpr bool CONTIG = DGB_BBE_CONTIG(NP);
     static constexpr int ES = CONTIG ? NP * 4 : NP * 4 + 2;  // element stride in shared memory (doubles); padded: ES/2 odd
     static constexpr int TILE = kTEE * ES;
     static constexpr int RS = (NFP + 15) / 16 * 16;  // row stride (bytes) of DeviceMesh::bbNbr16
@@ -335,7 +338,7 @@ void launchBBE(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
 StageKernel selectBBEKernel(int dim, int order) {
     StageKernel k;
 #define DGB_BBE(D, P) if (dim == D && order == P) { k.launch = &launchBBE<D, P>; k.name = "stage_bbe<" #D "," #P ">"; }
-    DGB_BBE(2, 1) DGB_BBE(2, 2) DGB_BBE(2, 3) DGB_BBE(3, 1)
+    DGB_BBE(2, 1) DGB_BBE(2, 2) DGB_BBE(2, 3) DGB_BBE(3, 1) DGB_BBE(3, 2)
 #undef DGB_BBE
     return k;
 }

@@ -74,8 +74,9 @@ CASES2 = [("square.msh", 1, (0.0, 0.0, 0.0)), ("square:5", 1, (30.0, 10.0, 0.0))
           ("sphere.msh", 1, (30.0, 10.0, 5.0))]
 
 
-# element-per-thread kernel (stage_bbe.cu, kernel 7): triangles of orders 1..3, tetrahedra of order 1
-CASES_E = [(n, o, v, 7) for (n, o, v) in CASES2 if o <= 3 and not (o > 1 and n.startswith(("cube", "sphere")))] + [("square:7", 2, (30.0, 10.0, 0.0), 7)]
+# element-per-thread kernel (stage_bbe.cu, kernel 7): triangles of orders 1..3, tetrahedra of orders 1 / 2
+CASES_E = [(n, o, v, 7) for (n, o, v) in CASES2 if o <= 3 and not (o > 1 and n.startswith(("cube", "sphere")))] + [
+    ("square:7", 2, (30.0, 10.0, 0.0), 7), ("cube:3", 2, (30.0, 10.0, 5.0), 7), ("sphere.msh", 2, (0.0, 0.0, 0.0), 7)]
 
 
 @pytest.mark.parametrize("name,order,v0,variant", [(n, o, v, 6) for (n, o, v) in CASES2] + CASES_E)
