@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
     constexpr bool kAccGlobal = DGB_BB2_ACC_GLOBAL != 0;
     constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
-    extern __shared__ __align__(128) unsigned char smemRaw2[];
+    DGB_DYNAMIC_SMEM(unsigned char, smemRaw2);  // 16-byte alignment suffices (bulk copies, cp.async, 128-bit accesses, 8-byte mbarriers)
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
     double* const sT = sA + C::TILE;                         // [NTB][8][TRS] traces of the faces in flight
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     bool haloReady = fx == nullptr;
     auto touchesBorder = [&](int tt) { return A.eBegin + (tt + 1) * kTE2 > fx->Kinterior; };
     auto waitPeers = [&]() {
+#ifndef DGB_EMULATE  // partitioned handles exist on devices only
         if (lane < fx->nPeers) {
             const unsigned long long* f = fx->myFlags + fx->waitRank[lane];
             unsigned long long t0, t1, v;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                 __nanosleep(100);
             }
         }
+#endif
         __syncwarp();
         haloReady = true;
     };
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         mbarInit2(&bars[0], 1);
         mbarInit2(&bars[1], 1);
         mbarInit2(&bars[2], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbarInitFence();
     }
     __syncwarp();
 
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
         for (int j = 0; j < DIM * DIM; ++j) G[j] = GN[j];
     }
     bulkWaitAll();  // every store of this warp, local and remote, is complete
+#ifndef DGB_EMULATE
     if (fx != nullptr) {
         // the last CTA to get here raises this rank's flag at every peer (release at system scope after all pushes)
         __syncwarp();
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
             if (lane < fx->nPeers) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fx->peerFlag[lane]), "l"(A.fxEpochSignal) : "memory");
         }
     }
+#endif
 }
 
 template <int DIM, int P>
@@ -495,6 +499,10 @@ void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = BB2Cfg<DIM, P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
+    const int nTiles = (nEl + kTE2 - 1) / kTE2;
+#ifdef DGB_EMULATE
+    const int grid = std::max(1, std::min(nTiles, 3));  // a few persistent "CTAs": every warp walks several tiles
+#else
     static KernelConfig kc;
     static int perSm[kMaxDevices] = {};
     const int numSm = configureKernel(kc, stageBB2Kernel<DIM, P>, C::SMEM, "stage_bb2");
@@ -508,9 +516,9 @@ void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
         }
         perSm[dev] = n;
     }
-    const int nTiles = (nEl + kTE2 - 1) / kTE2;
     const int grid = std::max(1, std::min(nTiles, (numSm - std::min(A.smReserve, numSm / 2)) * perSm[dev]));
-    stageBB2Kernel<DIM, P><<<grid, 32, C::SMEM, s>>>(M, A, nTiles);
+#endif
+    DGB_LAUNCH((stageBB2Kernel<DIM, P>), grid, 32, C::SMEM, s, M, A, nTiles);
 }
 
 // nodal <-> Bernstein conversion between the field-major nodal layout u[q][el*Np + n] (the reference's, the C ABI's) and the
@@ -518,7 +526,7 @@ void launchBB2(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
 // V^-1 in canonical order); fromBB: u_n = sum_i mat[n][i] c_i (columns of V in canonical order). in != out.
 __global__ void __launch_bounds__(256) convertBB2Kernel(const double* __restrict__ in, double* __restrict__ out, int64_t stride, int Np, int K,
                                                         const double* __restrict__ mat, int toBB) {
-    extern __shared__ double sx2[];  // [4][E*Np]
+    DGB_DYNAMIC_SMEM(double, sx2);  // [4][E*Np]
     const int E = 256 / Np;
     const int e0 = blockIdx.x * E;
     const int nE = min(E, K - e0);
@@ -570,14 +578,14 @@ StageKernel selectBB2Kernel(int dim, int order) {
 void launchConvertBB2(const double* in, double* out, int64_t stride, int Np, int K, const double* mat, bool toBB, cudaStream_t s) {
     if (K <= 0) return;
     const int E = 256 / Np;
-    convertBB2Kernel<<<(K + E - 1) / E, 256, (size_t)4 * E * Np * sizeof(double), s>>>(in, out, stride, Np, K, mat, toBB ? 1 : 0);
+    DGB_LAUNCH(convertBB2Kernel, (unsigned)((K + E - 1) / E), 256, (size_t)4 * E * Np * sizeof(double), s, in, out, stride, Np, K, mat, toBB ? 1 : 0);
 }
 
 void launchPackElementsBB2(const double* y, int Np, const int32_t* elems, int n, double* buf, cudaStream_t s) {
     const int64_t tot = 4ll * n * Np;
     if (tot <= 0) return;
     const unsigned blocks = (unsigned)std::min<int64_t>((tot + 255) / 256, 148 * 8);
-    packElementsBB2Kernel<<<blocks, 256, 0, s>>>(y, 4 * Np, elems, n, buf);
+    DGB_LAUNCH(packElementsBB2Kernel, blocks, 256, 0, s, y, 4 * Np, elems, n, buf);
 }
 
 }  // namespace dgb

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
     using C = BBECfg<DIM, P>;
     using SX = typename C::SX;
     constexpr int NP = C::NP, NFP = C::NFP, NF = C::NF, ES = C::ES, NV = SX::NV, ND = SX::ND;
-    extern __shared__ __align__(128) unsigned char smemRawE[];
+    DGB_DYNAMIC_SMEM(unsigned char, smemRawE);  // 16-byte alignment suffices (bulk copies, 128-bit accesses, 8-byte mbarriers)
     double* const sY = reinterpret_cast<double*>(smemRawE);  // stage input of the tile, [32][ES]
     double* const sU = sY + C::TILE;                          // u: loaded, combined in place, stored
     double* const sA = sU + C::TILE;                          // acc likewise
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
         mbarInit2(&bars[0], 1);
         mbarInit2(&bars[1], 1);
         mbarInit2(&bars[2], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbarInitFence();
     }
     __syncwarp();
 
@@ -315,6 +315,10 @@ void launchBBE(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
     using C = BBECfg<DIM, P>;
     const int nEl = A.eEnd - A.eBegin;
     if (nEl <= 0) return;
+    const int nTiles = (nEl + kTEE - 1) / kTEE;
+#ifdef DGB_EMULATE
+    const int grid = std::max(1, std::min(nTiles, 3));  // a few persistent "CTAs": every warp walks several tiles
+#else
     static KernelConfig kc;
     static int perSm[kMaxDevices] = {};
     const int numSm = configureKernel(kc, stageBBEKernel<DIM, P>, C::SMEM, "stage_bbe");
@@ -328,9 +332,9 @@ void launchBBE(const DeviceMesh& M, const StageArgs& A, cudaStream_t s) {
         }
         perSm[dev] = n;
     }
-    const int nTiles = (nEl + kTEE - 1) / kTEE;
     const int grid = std::max(1, std::min(nTiles, (numSm - std::min(A.smReserve, numSm / 2)) * perSm[dev]));
-    stageBBEKernel<DIM, P><<<grid, 32, C::SMEM, s>>>(M, A, nTiles);
+#endif
+    DGB_LAUNCH((stageBBEKernel<DIM, P>), grid, 32, C::SMEM, s, M, A, nTiles);
 }
 
 }  // namespace

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>  // host-side declarations; makes __global__ / __device__ / __forceinline__ harmless for g++
 
 #include <pthread.h>
+#include <sched.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +32,7 @@ struct Idx {
 struct State {
     pthread_barrier_t barrier;
     std::vector<double> smem;
+    std::vector<unsigned long long> shfl;  // one 8-byte slot per thread of the block (warp shuffles)
 };
 inline State*& current() {
     static State* s = nullptr;
@@ -43,6 +46,36 @@ static thread_local cuemu::Idx threadIdx, blockIdx;
 static cuemu::Idx blockDim, gridDim;
 
 #define __syncthreads() cuemu::syncthreads()
+// Warp-level primitives for kernels whose block is ONE warp (stage_bb2.cu, stage_bbe.cu): a warp barrier is the block barrier, a shuffle is an
+// exchange through one slot per thread between two barriers (every thread of the block must execute it, as the full-mask forms require).
+inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::syncthreads(); }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int srcLane, int width = 32) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    cuemu::State* st = cuemu::current();
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    st->shfl[threadIdx.x] = raw;
+    cuemu::syncthreads();
+    const unsigned src = (threadIdx.x / width) * width + (unsigned)(srcLane % width);
+    raw = st->shfl[src];
+    cuemu::syncthreads();
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int laneMask, int width = 32) { return __shfl_sync(mask, v, (int)((threadIdx.x % width) ^ (unsigned)laneMask), width); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long both = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((both >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+template <typename T>
+inline T __ldcg(const T* p) { return *p; }
+template <typename T>
+inline void __stcg(T* p, T v) { *p = v; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
@@ -54,6 +87,7 @@ template <typename Kernel, typename... Args>
 void launch(Kernel kernel, unsigned grid, unsigned block, size_t smemBytes, Args... args) {
     State st;
     st.smem.assign((smemBytes + sizeof(double) - 1) / sizeof(double) + (smemBytes == 0 ? 1 : 0), 0.0);  // exact size: AddressSanitizer builds see overruns
+    st.shfl.assign(block, 0ull);
     pthread_barrier_init(&st.barrier, nullptr, block);
     current() = &st;
     blockDim.x = block;

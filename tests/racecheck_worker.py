@@ -46,6 +46,20 @@ def main():
                 assert lib.bbe_eval_rhs(d, variant, u.ctypes.data_as(dp), rhs.ctypes.data_as(dp)) == 0
                 w = u.copy()
                 assert lib.bbe_run(d, variant, 1, w.ctypes.data_as(dp), 0.0, 1, len(idx), idx.ctypes.data_as(ip), 10.0, 1500.0, 0.3, 1.0) == 0
+    elif kind == "bb2":  # the product's default kernels: stage_bb2 (kernel 6) and stage_bbe (kernel 7), tetrahedra and triangles
+        lib.bb2e_run.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.c_int]
+        for cells, order, kernel in ((2, 4, 6), (2, 3, 6), (2, 2, 6), (3, 1, 7)):
+            mesh, u = mesh_and_state(pkg, cells, order, (3.0, 2.0, 1.0))
+            d = C.cast(mesh.desc_p, C.c_void_p)
+            for integrator, steps in ((2, 0), (1, 1), (0, 1)):
+                w = u.copy()
+                assert lib.bb2e_run(d, kernel, integrator, w.ctypes.data_as(dp), steps) == 0
+        for cells, order, kernel in ((3, 5, 6), (5, 1, 7), (4, 2, 7)):
+            model = pkg.Model.make_square(cells, -10.0, 10.0, order)
+            mesh = pkg.Mesh(model, pkg.Config())
+            mesh.set_physics(c0=343.0, rho0=1.225, v0=(3.0, 2.0, 0.0), dt=1e-5)
+            u = np.random.default_rng(0).standard_normal((4, mesh.N))
+            assert lib.bb2e_run(C.cast(mesh.desc_p, C.c_void_p), kernel, 1, u.ctypes.data_as(dp), 1) == 0
     elif kind == "curved":
         lib.cve_run.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
         mesh, u = mesh_and_state(pkg, 2, 2, (3.0, 2.0, 1.0), warp=(0.3, 0.4))

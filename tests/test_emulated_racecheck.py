@@ -56,7 +56,7 @@ def _run(kind, lib):
     return p.stderr.count("WARNING: ThreadSanitizer: data race")
 
 
-@pytest.mark.parametrize("kind,harness", [("bb", "bb_emulate.cpp"), ("curved", "curved_emulate.cpp"), ("generic", "generic_emulate.cpp")])
+@pytest.mark.parametrize("kind,harness", [("bb", "bb_emulate.cpp"), ("curved", "curved_emulate.cpp"), ("generic", "generic_emulate.cpp"), ("bb2", "bb2_emulate.cpp")])
 def test_no_shared_memory_race_in_the_emulated_kernels(tmp_path, kind, harness):
     lib = tmp_path / f"lib{kind}_tsan.so"
     _build(ROOT, harness, lib)
@@ -81,8 +81,26 @@ def test_the_race_check_sees_a_missing_barrier(tmp_path):
     assert _run("bb", lib) > 0
 
 
+def test_the_race_check_sees_a_missing_warp_barrier_in_stage_bb2(tmp_path):
+    """stage_bb2.cu with the warp barrier between the wait for a face's traces (copied by OTHER lanes) and their use removed."""
+    root = tmp_path / "src"
+    shutil.copytree(ROOT / "include", root / "include")
+    shutil.copytree(ROOT / "dgfem-acoustic_b200" / "csrc", root / "dgfem-acoustic_b200" / "csrc")
+    (root / "oracle").mkdir()
+    for f in ("cuda_emu.h", "emu_layout.h", "bb2_emulate.cpp"):
+        shutil.copy(ROOT / "oracle" / f, root / "oracle" / f)
+    cu = root / "dgfem-acoustic_b200" / "csrc" / "stage_bb2.cu"
+    text = cu.read_text()
+    marker = "may still travel)\n            __syncwarp();\n            double x[NFP];"
+    assert text.count(marker) == 1
+    cu.write_text(text.replace(marker, "may still travel)\n            double x[NFP];"))
+    lib = tmp_path / "libbb2_broken_tsan.so"
+    _build(root, "bb2_emulate.cpp", lib)
+    assert _run("bb2", lib) > 0
+
+
 @pytest.mark.skipif(ASAN is None, reason="libasan not available")
-@pytest.mark.parametrize("kind,harness", [("bb", "bb_emulate.cpp"), ("curved", "curved_emulate.cpp"), ("generic", "generic_emulate.cpp")])
+@pytest.mark.parametrize("kind,harness", [("bb", "bb_emulate.cpp"), ("curved", "curved_emulate.cpp"), ("generic", "generic_emulate.cpp"), ("bb2", "bb2_emulate.cpp")])
 def test_no_out_of_bounds_access_in_the_emulated_kernels(tmp_path, kind, harness):
     """AddressSanitizer build: the emulation sizes the dynamic shared memory exactly and the global arrays are host vectors, so an
     index that runs off a tile, a state array or a table is reported (the CPU counterpart of compute-sanitizer memcheck)."""
