@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
     constexpr bool kAccGlobal = DGB_BB2_ACC_GLOBAL != 0;
     constexpr bool kPerElement = C::PAD != 0;  // padded tiles: one bulk copy per element instead of one per tile
-    DGB_DYNAMIC_SMEM(unsigned char, smemRaw2);  // 16-byte alignment suffices (bulk copies, cp.async, 128-bit accesses, 8-byte mbarriers)
+    DGB_DYNAMIC_SMEM(double2, smemRaw2);  // 16-byte aligned: bulk copies, cp.async, 128-bit accesses, 8-byte mbarriers
     double* const sY = reinterpret_cast<double*>(smemRaw2);  // [8][NP][4] stage input of the tile; after the last face: u, combined in place, stored
     double* const sA = sY + C::TILE;                         // acc tile: loaded, combined in place, stored
     double* const sT = sA + C::TILE;                         // [NTB][8][TRS] traces of the faces in flight

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
     using C = BBECfg<DIM, P>;
     using SX = typename C::SX;
     constexpr int NP = C::NP, NFP = C::NFP, NF = C::NF, ES = C::ES, NV = SX::NV, ND = SX::ND;
-    DGB_DYNAMIC_SMEM(unsigned char, smemRawE);  // 16-byte alignment suffices (bulk copies, 128-bit accesses, 8-byte mbarriers)
+    DGB_DYNAMIC_SMEM(double2, smemRawE);  // 16-byte aligned: bulk copies, 128-bit accesses, 8-byte mbarriers
     double* const sY = reinterpret_cast<double*>(smemRawE);  // stage input of the tile, [32][ES]
     double* const sU = sY + C::TILE;                          // u: loaded, combined in place, stored
     double* const sA = sU + C::TILE;                          // acc likewise

@@ -11,8 +11,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 out_path = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out" / "r02_order_sweep.json"
 # (dim, order, cells, [kernel ids])   kernel 0 = automatic
-RUNS = [(3, 1, 56, [0]), (3, 2, 48, [0, 6]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0]),
-        (2, 1, 850, [0]), (2, 2, 600, [0]), (2, 3, 480, [0]), (2, 4, 400, [0]), (2, 5, 340, [0]), (2, 6, 300, [0])]
+RUNS = [(3, 1, 56, [0, 1, 6]), (3, 2, 48, [0, 1, 7]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0]),
+        (2, 1, 850, [0, 1, 6]), (2, 2, 600, [0, 1, 6]), (2, 3, 480, [0, 1, 7]), (2, 4, 400, [0, 1]), (2, 5, 340, [0, 1]), (2, 6, 300, [0, 1])]
 rows = []
 for dim, order, cells, kernels in RUNS:
     for k in kernels:
