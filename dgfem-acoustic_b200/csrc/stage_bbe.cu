@@ -29,6 +29,9 @@ constexpr int kTEE = 32;  // elements per tile = lanes
 #ifndef DGB_BBE_CONTIG
 #define DGB_BBE_CONTIG(NP) ((NP) == 3 || (NP) == 6 || (NP) == 10)
 #endif
+#ifndef DGB_BBE_PADDED_TRANSPORT
+#define DGB_BBE_PADDED_TRANSPORT 2
+#endif
 #ifndef DGB_BBE_WARPS
 #define DGB_BBE_WARPS(NP) ((NP) <= 3 ? 12 : (NP) <= 4 ? 10 : (NP) <= 6 ? 8 : 6)
 #endif
@@ -43,6 +46,10 @@ struct BBECfg {
     // (Np = 3) or 4-way (Np = 6, 10) and the kernel reaches 0.83 / 0.71 (Np = 10: 0.56 -> 0.60, tetrahedra of order 2: 0.47 either way —
     // stage_bb2 is the better kernel at Np = 10). Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way conflicts, 0.46) keeps the padded rows (0.57).
     static constexpr bool CONTIG = DGB_BBE_CONTIG(NP);
+    // how padded rows travel: 1 = one TMA bulk copy per element (request-rate bound, see above), 2 = warp-cooperative 16-byte cp.async into the padded
+    // rows (32 lanes x 16 B = 512 contiguous bytes of global memory per instruction) and 128-bit shared loads + coalesced 128-bit global stores back
+    static constexpr int TRANSPORT = CONTIG ? 0 : DGB_BBE_PADDED_TRANSPORT;
+    static constexpr int CPR = NP * 2;               // 16-byte chunks per element
     static constexpr int ES = CONTIG ? NP * 4 : NP * 4 + 2;  // element stride in shared memory (doubles); padded: ES/2 odd
     static constexpr int TILE = kTEE * ES;
     static constexpr int RS = (NFP + 15) / 16 * 16;  // row stride (bytes) of DeviceMesh::bbNbr16
@@ -109,7 +116,38 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
         }
     };
 
-    loadTile(sY, A.yin + (int64_t)(A.eBegin + t * kTEE) * NP * 4, nElems(t), &bars[0]);
+    // cooperative transport of padded rows (TRANSPORT == 2): chunk g of the tile = chunk g % CPR of element g / CPR
+    constexpr int kCoop = (kTEE * C::CPR + 31) / 32;
+    auto coopLoad = [&](double* dst, const double* src, int n) {
+        const int total = n * C::CPR;
+#pragma unroll
+        for (int k = 0; k < kCoop; ++k) {
+            const int g = k * 32 + lane;
+            if (g < total) {
+                const int er = g / C::CPR, c = g - er * C::CPR;
+                cpAsync16(dst + er * ES + c * 2, src + (int64_t)g * 2, 16u);
+            }
+        }
+    };
+    auto coopStore = [&](double* dst, const double* src, int n) {
+        const int total = n * C::CPR;
+#pragma unroll
+        for (int k = 0; k < kCoop; ++k) {
+            const int g = k * 32 + lane;
+            if (g < total) {
+                const int er = g / C::CPR, c = g - er * C::CPR;
+                *reinterpret_cast<double2*>(dst + (int64_t)g * 2) = *reinterpret_cast<const double2*>(src + er * ES + c * 2);
+            }
+        }
+    };
+    constexpr bool kCoopMode = C::TRANSPORT == 2;
+
+    if constexpr (kCoopMode) {
+        coopLoad(sY, A.yin + (int64_t)(A.eBegin + t * kTEE) * NP * 4, nElems(t));
+        cpCommit();
+    } else {
+        loadTile(sY, A.yin + (int64_t)(A.eBegin + t * kTEE) * NP * 4, nElems(t), &bars[0]);
+    }
     uint32_t phY = 0, phU = 0, phA = 0;
 
     for (;;) {
@@ -118,8 +156,14 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
         const int n = nElems(t);
         const int e0 = A.eBegin + t * kTEE;
         const int e = min(e0 + lane, A.eEnd - 1);  // lanes beyond the range repeat its last element (results not stored)
-        if (loadU) loadTile(sU, uSrc + (int64_t)e0 * NP * 4, n, &bars[1]);
-        if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, n, &bars[2]);
+        if constexpr (kCoopMode) {  // one cp.async group for u and acc (possibly empty: the group count per tile stays uniform)
+            if (loadU) coopLoad(sU, uSrc + (int64_t)e0 * NP * 4, n);
+            if (loadA) coopLoad(sA, A.acc + (int64_t)e0 * NP * 4, n);
+            cpCommit();
+        } else {
+            if (loadU) loadTile(sU, uSrc + (int64_t)e0 * NP * 4, n, &bars[1]);
+            if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, n, &bars[2]);
+        }
 
         // geometry of the lane's element: barycentric gradients
         double gl[4][3];
@@ -159,8 +203,13 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
         loadFace(std::integral_constant<int, 3>{});
 
         // own coefficients: shared memory -> registers, then the buffer is free for the next tile's stage input
-        mbarWait2(&bars[0], phY);
-        phY ^= 1;
+        if constexpr (kCoopMode) {
+            cpWaitAllButOne();  // the stage input (older than the u / acc group) has landed
+            __syncwarp();
+        } else {
+            mbarWait2(&bars[0], phY);
+            phY ^= 1;
+        }
         double c[4][NP];
         {
             const double* row = sY + lane * ES;
@@ -172,7 +221,12 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
             }
         }
         __syncwarp();
-        if (more) loadTile(sY, A.yin + (int64_t)(A.eBegin + tn * kTEE) * NP * 4, nElems(tn), &bars[0]);
+        if constexpr (kCoopMode) {
+            if (more) coopLoad(sY, A.yin + (int64_t)(A.eBegin + tn * kTEE) * NP * 4, nElems(tn));
+            cpCommit();
+        } else {
+            if (more) loadTile(sY, A.yin + (int64_t)(A.eBegin + tn * kTEE) * NP * 4, nElems(tn), &bars[0]);
+        }
 
         // volume term: out_q = -elevate( sum of directional derivatives )
         double out[4][NP];
@@ -259,8 +313,13 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
         doFace(std::integral_constant<int, 3>{});
 
         // fused RK update in the shared-memory rows of the RK registers, then bulk stores
-        if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
-        if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
+        if constexpr (kCoopMode) {
+            cpWaitAllButOne();  // u and acc have landed (the next tile's stage input may still travel)
+            __syncwarp();
+        } else {
+            if (loadU) { mbarWait2(&bars[1], phU); phU ^= 1; }
+            if (loadA) { mbarWait2(&bars[2], phA); phA ^= 1; }
+        }
         {
             double* const pu = sU + lane * ES;
             double* const pa = sA + lane * ES;
@@ -297,17 +356,25 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
                 }
             }
         }
-        fenceProxyAsync();
-        __syncwarp();
-        storeTile(uDst + (int64_t)e0 * NP * 4, sU, n);
-        if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, n);
-        bulkCommit();
-        if (!more) break;
-        bulkWaitRead();  // the stores have read sU / sA (every lane waits for the copies it issued)
-        __syncwarp();
+        if constexpr (kCoopMode) {
+            __syncwarp();
+            coopStore(uDst + (int64_t)e0 * NP * 4, sU, n);
+            if (storeA) coopStore(A.acc + (int64_t)e0 * NP * 4, sA, n);
+            if (!more) break;
+            __syncwarp();  // every lane has read the rows it stores before the next tile's copies overwrite them
+        } else {
+            fenceProxyAsync();
+            __syncwarp();
+            storeTile(uDst + (int64_t)e0 * NP * 4, sU, n);
+            if (storeA) storeTile(A.acc + (int64_t)e0 * NP * 4, sA, n);
+            bulkCommit();
+            if (!more) break;
+            bulkWaitRead();  // the stores have read sU / sA (every lane waits for the copies it issued)
+            __syncwarp();
+        }
         t = tn;
     }
-    bulkWaitAll();
+    if constexpr (kCoopMode) cpWaitAll(); else bulkWaitAll();
 }
 
 template <int DIM, int P>
