@@ -33,7 +33,9 @@ constexpr int kTEE = 32;  // elements per tile = lanes
 #define DGB_BBE_PADDED_TRANSPORT 2
 #endif
 #ifndef DGB_BBE_WARPS
-#define DGB_BBE_WARPS(NP) ((NP) <= 3 ? 12 : (NP) <= 4 ? 10 : (NP) <= 6 ? 8 : 6)
+// resident warps per SM the register allocation aims at; measured (profiles/r02/x_*): triangles of order 1 0.82 -> 0.89 with 16 instead of 12 warps, tetrahedra of
+// order 1 0.62 -> 0.66 with 12 instead of 10, triangles of order 2 0.71 -> 0.60 with 10 instead of 8 (spills)
+#define DGB_BBE_WARPS(NP) ((NP) <= 3 ? 16 : (NP) <= 4 ? 12 : (NP) <= 6 ? 8 : 6)
 #endif
 
 template <int DIM, int P>
@@ -44,7 +46,8 @@ struct BBECfg {
     // REQUEST RATE of the copy engine (160 requests of 96..192 bytes per tile: 0.58 / 0.59 of the HBM roof on triangles of order
     // 1 / 2); with ONE bulk copy per tile and array into unpadded rows the 128-bit accesses of the 32 lanes conflict 2-way
     // (Np = 3) or 4-way (Np = 6, 10) and the kernel reaches 0.83 / 0.71 (Np = 10: 0.56 -> 0.60, tetrahedra of order 2: 0.47 either way —
-    // stage_bb2 is the better kernel at Np = 10). Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way conflicts, 0.46) keeps the padded rows (0.57).
+    // stage_bb2 is the better kernel at Np = 10). Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way conflicts, 0.46 unpadded) keeps padded rows,
+    // filled by warp-cooperative cp.async instead of per-element bulk copies (TRANSPORT below: 0.57 -> 0.62).
     static constexpr bool CONTIG = DGB_BBE_CONTIG(NP);
     // how padded rows travel: 1 = one TMA bulk copy per element (request-rate bound, see above), 2 = warp-cooperative 16-byte cp.async into the padded
     // rows (32 lanes x 16 B = 512 contiguous bytes of global memory per instruction) and 128-bit shared loads + coalesced 128-bit global stores back
