@@ -52,6 +52,7 @@ __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group
 __device__ __forceinline__ void cpWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cpWaitAllButOne() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 __device__ __forceinline__ void mbarInitFence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 #else
 // emulated mbarrier word: bits 0..31 = outstanding transaction bytes (signed), bit 32 = phase
@@ -76,6 +77,7 @@ inline void bulkLoad(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigne
 }
 inline void bulkStore(void* gmemDst, const void* smemSrc, uint32_t bytes) { memcpy(gmemDst, smemSrc, bytes); }
 inline void bulkPrefetchL2(const void*, uint32_t) {}
+inline void prefetchL2(const void*) {}
 inline void bulkCommit() {}
 inline void bulkWaitRead() {}
 inline void bulkWaitAll() {}

@@ -168,6 +168,18 @@ __global__ void __launch_bounds__(32, BBECfg<DIM, P>::WARPS) stageBBEKernel(Devi
             if (loadA) loadTile(sA, A.acc + (int64_t)e0 * NP * 4, n, &bars[2]);
         }
 
+#ifdef DGB_BBE_META_PREFETCH  // measured (profiles/r02/y_*): 0.87 vs 0.90 (triangles, order 1), 0.73 vs 0.71 (order 2), 0.66 vs 0.66 (tetrahedra, order 1) — off
+        // the next tile's face metadata and inverse Jacobian: to L2 now (no register is spent), so that the dependent chain metadata -> neighbour
+        // gathers of the next tile starts from L2 hits
+        if (more) {
+            const int en = min(A.eBegin + tn * kTEE + lane, A.eEnd - 1);
+            prefetchL2(M.fflags + (int64_t)en * NF);
+            prefetchL2(M.fnbr + (int64_t)en * NF);
+            prefetchL2(M.fgeo + (int64_t)en * NF * 4);
+            prefetchL2(M.fgeo + (int64_t)en * NF * 4 + (NF * 4 - 1));
+            prefetchL2(M.Ginv + (int64_t)en * (DIM * DIM));
+        }
+#endif
         // geometry of the lane's element: barycentric gradients
         double gl[4][3];
         {
