@@ -474,6 +474,11 @@ def main():
                                   "peak_measured_this_run": fp64_now, "peak_measured_how": "dgb_measure_fp64_tflops: DFMA, 16 chains x 1024 threads per SM, best of 3"}},
             "clocks": clk.summary(),
         }
+        if eng.kernel_name.startswith(("stage_bb", "stage_bbe")):
+            # the Bernstein kernels execute ~0.3x the flops of the dense nodal operators this figure counts: it is kept for comparison with
+            # the DMMA kernels of round 1 and can exceed 1; HBM is the roof that binds these kernels
+            line["roofline"]["fp64"]["note"] = ("alg_flops count the DENSE nodal operators (SURVEY.md §8 d3); this kernel applies sparse Bernstein-Bezier operators "
+                                                "(~0.3x as many flops executed), so the fraction is a comparison with the dense kernels, not a pipe utilisation")
         if parity is not None:
             line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
