@@ -307,16 +307,25 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
             // lift inputs of face J for this lane's (element, field), straight into registers. With a = own - neighbour
             // (boundary: the neighbour trace is zero), S = n . a_v, the reference's fluxes read (bb_ops.h: faceInput)
             //   x_p = app a_p + aps S,   x_v = b a_v + n_v (c a_p + d S):
-            // every lane forms a for its own field, the quad exchanges a_p and S by shuffles
-            double A1, A2, A3, nq;
+            // every lane forms a for its own field; the quad needs two scalars per trace coefficient, S (the pressure lane) and g = c a_p + d S (the
+            // velocity lanes), and gets them in TWO exchange rounds: with m = mu a (mu = 1 for p, n_v for the velocities)
+            //   round 1 (xor 1): lane p <-> v_x, v_y <-> v_z            r1 = the partner's m
+            //   round 2 (xor 2): send = P m + Q r1 with (P, Q) = (c, d) for p, (d, c) for v_x, (1, 1) for v_y, v_z
+            //                    p receives m_vy + m_vz (S = r1 + r2); v_y, v_z receive c a_p + d m_vx; v_x receives m_vy + m_vz
+            //   x = A1' a + E1 r1 + E2 r2  with lane-dependent coefficients (the own term d n_v m of g is folded into A1')
+            // — one instruction stream for interior, absorbing and reflecting faces, the same arithmetic for an element wherever it sits in a tile.
+            double A1, E1, E2, mu, Pq, Qq;
             {
                 const double2* fc = reinterpret_cast<const double2*>(sFc + (lf * 8 + el) * C::FCS);
-                const double2 c0 = fc[0], c1 = fc[1], c2 = fc[2], c3 = fc[3];
+                const double2 c0 = fc[0], c1 = fc[1], c2 = fc[2], c3 = fc[3];  // (app, aps) (b, c) (d, n0) (n1, n2)
                 const double nv = q == 1 ? c2.y : q == 2 ? c3.x : c3.y;
-                nq = q == 0 ? 0.0 : nv;
-                A1 = q == 0 ? c0.x : c1.x;
-                A2 = q == 0 ? 0.0 : nv * c1.y;
-                A3 = q == 0 ? c0.y : nv * c2.x;
+                const double nd = nv * c2.x;
+                mu = q == 0 ? 1.0 : nv;
+                Pq = q == 0 ? c1.y : q == 1 ? c2.x : 1.0;
+                Qq = q == 0 ? c2.x : q == 1 ? c1.y : 1.0;
+                E1 = q == 0 ? c0.y : q == 1 ? nv * c1.y : nd;
+                E2 = q == 0 ? c0.y : q == 1 ? nd : nv;
+                A1 = q == 0 ? c0.x : c1.x + nd * nv;
             }
             if constexpr (C::NTB == 2) cpWaitAllButOne(); else cpWaitAll();  // the traces of this face have landed (the next face's may still travel)
             __syncwarp();
@@ -327,11 +336,10 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
 #pragma unroll
             for (int b = 0; b < NFP; ++b) {
                 const double a = own[M.bbOwn[J][b] * 4] - tr[b * 4];
-                const double c = nq * a;
-                const double s1 = c + __shfl_xor_sync(FULL, c, 1);
-                const double S = s1 + __shfl_xor_sync(FULL, s1, 2);
-                const double ap = __shfl_sync(FULL, a, 0, 4);
-                x[b] = A1 * a + (A2 * ap + A3 * S);
+                const double m = mu * a;
+                const double r1 = __shfl_xor_sync(FULL, m, 1);
+                const double r2 = __shfl_xor_sync(FULL, Pq * m + Qq * r1, 2);
+                x[b] = A1 * a + (E1 * r1 + E2 * r2);
             }
             __syncwarp();  // this trace buffer is free: the traces of face (this + NTB) travel while this face and the next are lifted
             if constexpr (C::NTB == 2) {
