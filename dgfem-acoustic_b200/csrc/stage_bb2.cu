@@ -28,6 +28,8 @@
 //
 // Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded at orders 2 / 3 / 5) | one face's traces |
 // face coefficients | 3 mbarriers.
+#include <type_traits>
+
 #include "bb_ops.h"
 #include "dgb_async.cuh"
 #include "dgb_device.cuh"
@@ -44,6 +46,11 @@ constexpr int kTE2 = 8;  // elements per tile: 8 elements x 4 fields = the 32 la
                               // u at the start of the tile and the stage-input buffer the NEXT tile's input after the last face: no wait for either.
                               // Measured (profiles/r02/t_*): the 70 8-byte global accesses per thread cost far more than the two waits they remove —
                               // tetrahedra of order 4: 1.85 vs 1.46 ms, order 5: 0.99 vs 0.77; triangles of order 3 / 4: 2..5 % faster. Off.
+#endif
+#ifndef DGB_BB2_OWN_UNROLLED
+#define DGB_BB2_OWN_UNROLLED 0  // 1 (experiment): own-trace offsets as immediates, one copy of the input loop per face. Measured (profiles/r02/ab_*): the tile loop grows
+                                // from 4 472 to 6 832 instructions and the kernel slows from 1.46 to 1.63 ms at order 4 (instruction caches of 8 warps in different
+                                // phases) — the table look-up stays
 #endif
 #ifndef DGB_BB2_TRACE_BUFFERS
 #define DGB_BB2_TRACE_BUFFERS 0  // 0: per configuration (BB2Cfg::NTB); 1 / 2: forced (experiments)
@@ -108,6 +115,16 @@ __device__ __forceinline__ void fieldVolumeInterleaved(int q, const double* col,
 #pragma unroll
     for (int i = 0; i < NP; ++i) out[i] = 0.0;
     SX::elevate(t, -1.0, out);
+}
+
+// canonical volume index of coefficient b (canonical face order) of canonical face J — what DeviceMesh::bbOwn tabulates
+template <int DIM, int N, int J>
+__host__ __device__ constexpr int bb2OwnIndex(int b) {
+    if (DIM == 2) return bb::d2::layerIdx<N, (J < 3 ? J : 0)>(0, b);
+    for (int b1 = 0; b1 <= N; ++b1)
+        for (int b2 = 0; b2 <= N - b1; ++b2)
+            if (bb::fidx(N, b1, b2) == b) return bb::layerIdx<N, J>(0, b1, b2);
+    return 0;
 }
 
 // resident warps per SM the register allocation aims at (the shared memory of a warp allows about as many)
@@ -333,6 +350,26 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
             const double* const own = sY + el * ES + q;
             double* const tbuf = sT + tb * (kTE2 * TRS);
             const double* const tr = tbuf + el * TRS + q;
+#if DGB_BB2_OWN_UNROLLED
+            // the own-trace offsets as immediates: one copy of the loop per face (no table look-up, no address arithmetic; more code)
+            auto inputs = [&](auto Jc) {
+                constexpr int JJ = decltype(Jc)::value;
+#pragma unroll
+                for (int b = 0; b < NFP; ++b) {
+                    const double a = own[bb2OwnIndex<DIM, P, (JJ < NF ? JJ : 0)>(b) * 4] - tr[b * 4];
+                    const double m = mu * a;
+                    const double r1 = __shfl_xor_sync(FULL, m, 1);
+                    const double r2 = __shfl_xor_sync(FULL, Pq * m + Qq * r1, 2);
+                    x[b] = A1 * a + (E1 * r1 + E2 * r2);
+                }
+            };
+            switch (J) {  // warp-uniform
+                case 0: inputs(std::integral_constant<int, 0>{}); break;
+                case 1: inputs(std::integral_constant<int, 1>{}); break;
+                case 2: inputs(std::integral_constant<int, 2>{}); break;
+                default: inputs(std::integral_constant<int, 3>{}); break;
+            }
+#else
 #pragma unroll
             for (int b = 0; b < NFP; ++b) {
                 const double a = own[M.bbOwn[J][b] * 4] - tr[b * 4];
@@ -341,6 +378,7 @@ __global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB
                 const double r2 = __shfl_xor_sync(FULL, Pq * m + Qq * r1, 2);
                 x[b] = A1 * a + (E1 * r1 + E2 * r2);
             }
+#endif
             __syncwarp();  // this trace buffer is free: the traces of face (this + NTB) travel while this face and the next are lifted
             if constexpr (C::NTB == 2) {
                 tb ^= 1;
