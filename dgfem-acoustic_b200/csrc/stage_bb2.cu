@@ -128,10 +128,23 @@ __host__ __device__ constexpr int bb2OwnIndex(int b) {
 }
 
 // resident warps per SM the register allocation aims at (the shared memory of a warp allows about as many)
-__host__ __device__ constexpr int bb2WarpsPerSm(int np) { return np <= 3 ? 24 : np <= 10 ? 16 : np <= 21 ? 12 : np <= 35 ? 8 : 6; }
+// measured (profiles/r02/ac_*, ad_*): at Np = 10 tetrahedra (order 2) want 16 warps (0.60; 12: 0.54, 20: 0.56), triangles (order 3) 20 (0.72; 16: 0.69)
+#ifndef DGB_BB2_W2D_NP15
+#define DGB_BB2_W2D_NP15 16  // triangles of order 4: 0.80 -> 0.87 with 16 instead of 12 warps
+#endif
+#ifndef DGB_BB2_W2D_NP21
+#define DGB_BB2_W2D_NP21 12  // triangles of order 5: 0.87 (14 warps: 0.81, spills)
+#endif
+#ifndef DGB_BB2_W2D_NP28
+#define DGB_BB2_W2D_NP28 10  // triangles of order 6: 0.80 -> 0.84 with 10 instead of 8
+#endif
+#define DGB_BB2_WARPS(DIM, NP)                                                                                                                          \
+    ((NP) <= 3 ? 24 : (NP) < 10 ? 16 : (NP) == 10 ? ((DIM) == 2 ? 20 : 16) : ((DIM) == 2 && (NP) == 15) ? DGB_BB2_W2D_NP15 : ((DIM) == 2 && (NP) == 21) ? DGB_BB2_W2D_NP21 \
+     : ((DIM) == 2 && (NP) == 28) ? DGB_BB2_W2D_NP28 : (NP) <= 21 ? 12 : (NP) <= 35 ? 8 : 6)
+__host__ __device__ constexpr int bb2WarpsPerSm(int dim, int np) { return DGB_BB2_WARPS(dim, np); }
 
 template <int DIM, int P>
-__global__ void __launch_bounds__(32, bb2WarpsPerSm(BB2Cfg<DIM, P>::NP)) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
+__global__ void __launch_bounds__(32, bb2WarpsPerSm(DIM, BB2Cfg<DIM, P>::NP)) stageBB2Kernel(DeviceMesh M, StageArgs A, int nTiles) {
     using C = BB2Cfg<DIM, P>;
     using SX = typename C::SX;
     constexpr int NP = C::NP, NFP = C::NFP, TRS = C::TRS, ES = C::ES, NF = C::NF;
