@@ -18,16 +18,19 @@
 //       - the tile of the stage input, and the RK registers u / acc of the tile, arrive by TMA bulk copies
 //         (cp.async.bulk, mbarrier complete_tx) — no LSU instruction, no register, no L1 wavefront;
 //       - the results leave by TMA bulk stores straight from the shared-memory tiles they were combined in;
-//       - the neighbour traces of ONE face at a time are gathered with 16-byte cp.async (zero-filled on boundary faces),
-//         lane (element, slot) fetching its own element's trace (the per-element address work is done once per face),
-//         issued one lift ahead of their use;
-//       - the next tile's stage input is requested as soon as the last face has read the current one, its face metadata
-//         and inverse Jacobian travel in registers one tile ahead.
-//   * 6 warps per SM at order 4 (33 KB of shared memory each): the latency that occupancy hid badly is hidden by the
-//     copies in flight instead.
+//       - the neighbour traces are gathered face by face with 16-byte cp.async (zero-filled on boundary faces), lane
+//         (element, slot) fetching its own element's trace (the per-element address work is done once per face), into one
+//         or two trace buffers: with two, the traces of face s + 2 travel while faces s and s + 1 are lifted;
+//       - the next tile's stage input is requested as soon as the stores have read the tile buffers (it sits in L2 by then:
+//         prefetched at the start of the tile), its face metadata and inverse Jacobian travel in registers one tile ahead.
+//   * 8 warps per SM at order 4 (27.7 KB of shared memory each, 242 registers): the latency that occupancy hid badly is
+//     hidden by the copies in flight instead.
+//   * Tetrahedra of orders 1..5 and triangles of orders 1..6 (bb::Simplex<DIM, N>); the halo exchange of partitioned handles is
+//     part of the kernel (bulk stores into the peers' halo slots, last CTA signals, border tiles wait).
 //
-// Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded at orders 2 / 3 / 5) | one face's traces |
-// face coefficients | 3 mbarriers.
+// Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded where Np*4 != 4 mod 8) | one or two faces'
+// traces | face coefficients | 3 mbarriers.
+// The file also runs on the CPU: oracle/bb2_emulate.cpp includes it behind oracle/cuda_emu.h (DGB_EMULATE; test infrastructure).
 #include <type_traits>
 
 #include "bb_ops.h"
