@@ -554,7 +554,7 @@ void createImpl(const dgb_desc* d, const int32_t* elPart, int rank, int nranks, 
         h->bbKernel = curved ? StageKernel{} : selectBBKernel(dim, d->order);
         const StageKernel bb2Candidate = curved ? StageKernel{} : selectBB2Kernel(dim, d->order);
         if (curved) h->bbWhyNot = "curved elements";
-        else if (!h->bbKernel.launch && !bb2Candidate.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra of orders 1..5, triangles of orders 1..6)";
+        else if (!h->bbKernel.launch && !bb2Candidate.launch) h->bbWhyNot = "no Bernstein-Bezier kernel for this dimension / order (tetrahedra and triangles of orders 1..6)";
         else {
             try {
                 const bb::Setup S = bb::buildSetup(d);

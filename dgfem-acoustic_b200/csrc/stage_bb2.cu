@@ -25,7 +25,7 @@
 //         prefetched at the start of the tile), its face metadata and inverse Jacobian travel in registers one tile ahead.
 //   * 8 warps per SM at order 4 (27.7 KB of shared memory each, 242 registers): the latency that occupancy hid badly is
 //     hidden by the copies in flight instead.
-//   * Tetrahedra of orders 1..5 and triangles of orders 1..6 (bb::Simplex<DIM, N>); the halo exchange of partitioned handles is
+//   * Tetrahedra and triangles of orders 1..6 (bb::Simplex<DIM, N>; tetrahedra of order 6 — 84 coefficients per thread — spill ~300 bytes); the halo exchange of partitioned handles is
 //     part of the kernel (bulk stores into the peers' halo slots, last CTA signals, border tiles wait).
 //
 // Shared memory of a warp: stage-input / u tile | acc tile (2 x 8*Np*32 B, padded where Np*4 != 4 mod 8) | one or two faces'
@@ -143,7 +143,7 @@ __host__ __device__ constexpr int bb2OwnIndex(int b) {
 #endif
 #define DGB_BB2_WARPS(DIM, NP)                                                                                                                          \
     ((NP) <= 3 ? 24 : (NP) < 10 ? 16 : (NP) == 10 ? ((DIM) == 2 ? 20 : 16) : ((DIM) == 2 && (NP) == 15) ? DGB_BB2_W2D_NP15 : ((DIM) == 2 && (NP) == 21) ? DGB_BB2_W2D_NP21 \
-     : ((DIM) == 2 && (NP) == 28) ? DGB_BB2_W2D_NP28 : (NP) <= 21 ? 12 : (NP) <= 35 ? 8 : 6)
+     : ((DIM) == 2 && (NP) == 28) ? DGB_BB2_W2D_NP28 : (NP) <= 21 ? 12 : (NP) <= 35 ? 8 : (NP) <= 56 ? 6 : 4)
 __host__ __device__ constexpr int bb2WarpsPerSm(int dim, int np) { return DGB_BB2_WARPS(dim, np); }
 
 template <int DIM, int P>
@@ -631,7 +631,7 @@ __global__ void packElementsBB2Kernel(const double* __restrict__ y, int per, con
 StageKernel selectBB2Kernel(int dim, int order) {
     StageKernel k;
 #define DGB_BB2(D, P) if (dim == D && order == P) { k.launch = &launchBB2<D, P>; k.name = "stage_bb2<" #D "," #P ">"; }
-    DGB_BB2(3, 1) DGB_BB2(3, 2) DGB_BB2(3, 3) DGB_BB2(3, 4) DGB_BB2(3, 5)
+    DGB_BB2(3, 1) DGB_BB2(3, 2) DGB_BB2(3, 3) DGB_BB2(3, 4) DGB_BB2(3, 5) DGB_BB2(3, 6)
     DGB_BB2(2, 1) DGB_BB2(2, 2) DGB_BB2(2, 3) DGB_BB2(2, 4) DGB_BB2(2, 5) DGB_BB2(2, 6)
 #undef DGB_BB2
     return k;

@@ -157,12 +157,12 @@ int64_t dgb_launch_count(dgb_handle* h);      /* kernels launched by this handle
 double dgb_measure_fp64_tflops(dgb_handle* h);
 /* Options (all integers):
  *   "kernel"   0 automatic (default: a Bernstein-Bezier kernel wherever one exists — 7 on triangles of order 1 / 2 and tetrahedra
- *              of order 1, 6 on triangles of order 3..6 and tetrahedra of order 2..5 — else the CUDA-core kernel),
+ *              of order 1, 6 on triangles of order 3..6 and tetrahedra of order 2..6 — else the CUDA-core kernel),
  *              1 generic CUDA cores, 2 tiled DMMA, 3 warp-specialised DMMA (zero mean flow),
  *              4 / 5 first-generation Bernstein-Bezier kernels (tetrahedra of order 2..5; 5 = face-sequential schedule;
  *              "bb_tile": 32 / 16 / 8 elements per CTA), 6 second-generation Bernstein-Bezier kernel (csrc/stage_bb2.cu:
- *              tetrahedra of order 1..5, triangles of order 1..6), 7 the same arithmetic with one thread per element
- *              (csrc/stage_bbe.cu: triangles of order 1..3, tetrahedra of order 1). A kernel that does not exist for the
+ *              tetrahedra and triangles of order 1..6), 7 the same arithmetic with one thread per element
+ *              (csrc/stage_bbe.cu: triangles of order 1..3, tetrahedra of order 1 / 2). A kernel that does not exist for the
  *              mesh is refused with DGB_ERR_UNSUPPORTED.
  *              With a Bernstein kernel the state is kept as Bernstein coefficients on the device; dgb_set_state /
  *              dgb_get_state / probes / receivers / sources convert.

@@ -15,7 +15,7 @@ ONLY = None
 if "--only" in sys.argv:
     ONLY = {tuple(int(x) for x in item.split(":")) for item in sys.argv[sys.argv.index("--only") + 1].split(",")}
 # (dim, order, cells, [kernel ids])   kernel 0 = automatic
-RUNS = [(3, 1, 56, [0, 1, 6]), (3, 2, 48, [0, 1, 7]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0]),
+RUNS = [(3, 1, 56, [0, 1, 6]), (3, 2, 48, [0, 1, 7]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0, 1]),
         (2, 1, 850, [0, 1, 6]), (2, 2, 600, [0, 1, 6]), (2, 3, 480, [0, 1, 7]), (2, 4, 400, [0, 1]), (2, 5, 340, [0, 1]), (2, 6, 300, [0, 1])]
 rows = []
 if ONLY is not None and out_path.exists():

@@ -58,7 +58,7 @@ def _close(got, want, u):
     (6, "cube:2", 4, (0.0, 0.0, 0.0), 1), (6, "cube:2", 3, (30.0, 10.0, -5.0), 1), (6, "cube:2", 2, (0.0, 0.0, 0.0), 1), (6, "square:3", 5, (3.0, -2.0, 0.0), 1),
     (6, "square:4", 3, (0.0, 0.0, 0.0), 1), (6, "cube:1", 5, (1.0, 2.0, 3.0), 1), (6, "cube:3", 4, (30.0, 10.0, -5.0), 1), (6, "cube:3", 1, (0.0, 0.0, 0.0), 2),
     (6, "square:4", 4, (30.0, 10.0, 0.0), 1), (6, "square:3", 6, (0.0, 0.0, 0.0), 1), (6, "square:6", 2, (3.0, 2.0, 0.0), 1), (6, "square:5", 1, (0.0, 0.0, 0.0), 2),
-    (7, "cube:2", 2, (0.0, 0.0, 0.0), 1), (7, "square_reflection.msh", 2, (30.0, 10.0, 0.0), 1)])
+    (7, "cube:2", 2, (0.0, 0.0, 0.0), 1), (7, "square_reflection.msh", 2, (30.0, 10.0, 0.0), 1), (6, "cube:1", 6, (3.0, 2.0, 1.0), 1), (6, "cube:2", 6, (0.0, 0.0, 0.0), 1)])
 def test_emulated_kernels_equal_the_oracle(pkg, oracle_mod, emu, mesh_dir, kernel, name, order, v0, steps):
     mesh, u = _case(pkg, mesh_dir, name, order, v0)
     d = C.cast(mesh.desc_p, C.c_void_p)

@@ -71,7 +71,7 @@ def test_rhs_and_rk4(pkg, oracle_mod, mesh_dir, name, order, v0, variant):
 # second-generation kernel only: triangles of orders 1..6 (the reference's 2D meshes, a refined square with partial tiles) and tetrahedra of order 1
 CASES2 = [("square.msh", 1, (0.0, 0.0, 0.0)), ("square:5", 1, (30.0, 10.0, 0.0)), ("disk.msh", 2, (0.0, 0.0, 0.0)), ("square_reflection.msh", 3, (30.0, 10.0, 0.0)),
           ("square.msh", 4, (0.0, 0.0, 0.0)), ("square:3", 5, (3.0, -2.0, 0.0)), ("disk.msh", 6, (0.0, 0.0, 0.0)), ("cube:3", 1, (0.0, 0.0, 0.0)),
-          ("sphere.msh", 1, (30.0, 10.0, 5.0))]
+          ("sphere.msh", 1, (30.0, 10.0, 5.0)), ("cube:2", 6, (30.0, 10.0, 5.0)), ("cube:3", 6, (0.0, 0.0, 0.0))]
 
 
 # element-per-thread kernel (stage_bbe.cu, kernel 7): triangles of orders 1..3, tetrahedra of orders 1 / 2
@@ -219,5 +219,7 @@ def test_unsupported_combinations_fail_loudly(pkg, mesh_dir):
     mesh6 = pkg.Mesh(pkg.Model.make_cube(2, -10.0, 10.0, 6), pkg.Config())
     eng6 = pkg.Engine(mesh6)
     with pytest.raises(pkg.DgbError):
-        eng6.set_option("kernel", 4)  # order 6: not instantiated
+        eng6.set_option("kernel", 4)  # order 6: no first-generation kernel
+    with pytest.raises(pkg.DgbError):
+        eng6.set_option("kernel", 7)  # nor an element-per-thread one
     eng6.close()
