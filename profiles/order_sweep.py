@@ -18,8 +18,9 @@ if "--only" in sys.argv:
 RUNS = [(3, 1, 56, [0, 1, 6]), (3, 2, 48, [0, 1, 7]), (3, 3, 48, [0, 3, 1]), (3, 4, 62, [0, 3]), (3, 5, 40, [0, 1]), (3, 6, 36, [0, 1]),
         (2, 1, 850, [0, 1, 6]), (2, 2, 600, [0, 1, 6]), (2, 3, 480, [0, 1, 7]), (2, 4, 400, [0, 1]), (2, 5, 340, [0, 1]), (2, 6, 300, [0, 1])]
 rows = []
-if ONLY is not None and out_path.exists():
-    rows = [r for r in json.loads(out_path.read_text())["rows"] if (r["dim"], r["order"]) not in ONLY]
+if ONLY is not None:  # gpurun_out/ does not travel to the GPU box: fall back to the committed table
+    base = out_path if out_path.exists() else ROOT / "profiles" / "r02_order_sweep.json"
+    rows = [r for r in json.loads(base.read_text())["rows"] if (r["dim"], r["order"]) not in ONLY]
 for dim, order, cells, kernels in RUNS:
     if ONLY is not None and (dim, order) not in ONLY:
         continue
