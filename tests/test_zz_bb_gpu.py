@@ -205,6 +205,31 @@ def test_sources_probes_receivers_in_bernstein_mode(pkg, oracle_mod, mesh_dir, v
     eng.close()
 
 
+def test_switching_between_the_two_default_kernels_keeps_the_resident_state(pkg, oracle_mod, mesh_dir):
+    """stage_bbe (kernel 7) and stage_bb2 (kernel 6) share the interleaved Bernstein representation: switching converts nothing."""
+    mesh = _mesh(pkg, mesh_dir, "square.msh", 2, (30.0, 10.0, 0.0))
+    u0 = _state(mesh, 2)
+    eng = pkg.Engine(mesh)
+    assert eng.kernel_name == "stage_bbe<2,2>" and eng.get_option("representation") == 2
+    eng.set_state(u0)
+    t = eng.run(pkg.RUNGE_KUTTA, 0.0, 4)
+    eng.set_option("kernel", 6)
+    assert eng.kernel_name == "stage_bb2<2,2>" and eng.get_option("representation") == 2
+    t = eng.run(pkg.RUNGE_KUTTA, t, 3)
+    eng.set_option("kernel", 1)            # nodal kernel: one conversion
+    assert eng.get_option("representation") == 0
+    t = eng.run(pkg.RUNGE_KUTTA, t, 2)
+    eng.set_option("kernel", 0)            # back to the automatic choice
+    assert eng.kernel_name == "stage_bbe<2,2>"
+    eng.run(pkg.RUNGE_KUTTA, t, 3)
+    got = eng.get_state()
+    want = u0.copy()
+    oracle_mod.Oracle(mesh).run(oracle_mod.Oracle.OPERATOR, pkg.RUNGE_KUTTA, want, 0.0, 12)
+    for q in range(4):
+        assert rel_l2(got[q], want[q]) < TOL
+    eng.close()
+
+
 def test_unsupported_combinations_fail_loudly(pkg, mesh_dir):
     mesh2 = pkg.Mesh(pkg.Model.open_msh(mesh_dir / "square.msh", 2), pkg.Config())
     eng2 = pkg.Engine(mesh2)
