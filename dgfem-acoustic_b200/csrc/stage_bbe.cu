@@ -49,6 +49,8 @@ struct BBECfg {
     // stage_bb2 is the better kernel at Np = 10). Np = 4 (tetrahedra of order 1: 128-byte rows, 8-way conflicts, 0.46 unpadded) keeps padded rows,
     // filled by warp-cooperative cp.async instead of per-element bulk copies (TRANSPORT below: 0.57 -> 0.62).
     static constexpr bool CONTIG = DGB_BBE_CONTIG(NP);
+    // (The cooperative transport below for EVERY row size loses to the single bulk copy with conflicts: 0.72 vs 0.90 at Np = 3, 0.67 vs 0.72 at Np = 6,
+    // 0.56 vs 0.60 at Np = 10 — profiles/r02/ae_*.)
     // how padded rows travel: 1 = one TMA bulk copy per element (request-rate bound, see above), 2 = warp-cooperative 16-byte cp.async into the padded
     // rows (32 lanes x 16 B = 512 contiguous bytes of global memory per instruction) and 128-bit shared loads + coalesced 128-bit global stores back
     static constexpr int TRANSPORT = CONTIG ? 0 : DGB_BBE_PADDED_TRANSPORT;
