@@ -141,9 +141,12 @@ __host__ __device__ constexpr int bb2OwnIndex(int b) {
 #ifndef DGB_BB2_W2D_NP28
 #define DGB_BB2_W2D_NP28 10  // triangles of order 6: 0.80 -> 0.84 with 10 instead of 8
 #endif
+#ifndef DGB_BB2_W3D_NP20
+#define DGB_BB2_W3D_NP20 12  // tetrahedra of order 3: 0.71 (10 warps: 0.69, 14: 0.63)
+#endif
 #define DGB_BB2_WARPS(DIM, NP)                                                                                                                          \
     ((NP) <= 3 ? 24 : (NP) < 10 ? 16 : (NP) == 10 ? ((DIM) == 2 ? 20 : 16) : ((DIM) == 2 && (NP) == 15) ? DGB_BB2_W2D_NP15 : ((DIM) == 2 && (NP) == 21) ? DGB_BB2_W2D_NP21 \
-     : ((DIM) == 2 && (NP) == 28) ? DGB_BB2_W2D_NP28 : (NP) <= 21 ? 12 : (NP) <= 35 ? 8 : (NP) <= 56 ? 6 : 4)
+     : ((DIM) == 2 && (NP) == 28) ? DGB_BB2_W2D_NP28 : ((DIM) == 3 && (NP) == 20) ? DGB_BB2_W3D_NP20 : (NP) <= 21 ? 12 : (NP) <= 35 ? 8 : (NP) <= 56 ? 6 : 4)
 __host__ __device__ constexpr int bb2WarpsPerSm(int dim, int np) { return DGB_BB2_WARPS(dim, np); }
 
 template <int DIM, int P>
