@@ -11,12 +11,14 @@
 * `e2e`    : the user-facing call sequence through the C ABI from HOST buffers: dgb_set_state (pinned host ->
              device), dgb_run(K steps), dgb_get_state (device -> pinned host), timed with a host clock around
              the three synchronous calls, max over ranks.
-* `roofline`: the stage kernel against the HBM roof (algorithmic bytes) and, because order 4 is
-             FP64-bound, against the FP64 roof measured by profiles/microbench (DMMA/DFMA 37.1 TFLOP/s).
+* `roofline`: the stage kernel against the measured HBM roof (algorithmic bytes; `traffic` = DRAM bytes of the
+             committed ncu capture of the same kernel) and, for comparison with the dense-operator kernels of round 1, against
+             the FP64 roof (dense flops; the Bernstein kernels of the default path execute ~0.3x as many, see the `note`).
 * `cpu_baseline` / `--impl reference`: the reference's OWN sources (oracle/_ref/dgalerkin_ref) on the host cores
              on a bounded sample of the same workload (falls back to the oracle's faithful mode, kind "port").
-N > 1 (launched by torchrun): the same mesh is partitioned over the ranks (recursive coordinate bisection), halo
-traces are exchanged with NCCL once per stage, overlapped with the interior elements ("strong" scaling).
+N > 1 (launched by torchrun): the same mesh is partitioned over the ranks (recursive coordinate bisection or METIS); the halo
+exchange is fused into the stage kernel (peer-to-peer bulk stores over NVLink, `--exchange 0` = NCCL send/recv); "strong"
+scaling; the line carries a `parity` object (a fixed sub-case run partitioned and on one GPU in the same process).
 """
 from __future__ import annotations
 
